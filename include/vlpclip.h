@@ -1,0 +1,118 @@
+/* vlpclip.h -- C ABI of the B200-native fused CLIP (symmetric InfoNCE) head.
+ *
+ * Drop-in boundary for the hot path of
+ *   /root/reference/src/models/pretrain/VisionLanguageModule.py
+ *     :448-453  projection + L2-normalise of both streams      -> vlpclip_project_normalize_*
+ *     :456-459  clamp(exp(logit_scale)) scaled N x N similarity -> fused into vlpclip_lse_fwd / vlpclip_grad
+ *     :550-552  row / column cross-entropy                      -> vlpclip_lse_fwd + vlpclip_lse_merge + vlpclip_loss_reduce
+ *     autograd of the above (triggered after :645)              -> vlpclip_grad, vlpclip_normalize_bwd
+ *     :364-439  retrieval metrics (the "next" row f1)           -> vlpclip_topk_rows
+ *
+ * The reference has no FFI of its own (pure Python over torch ops); the Python host side binds
+ * these symbols with ctypes. Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocator); the library
+ *     never allocates persistent device memory and never frees;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = ok, negative = error; vlpclip_last_error() returns a thread-local message;
+ *   - the N x N logit matrix is never written to global memory by any entry point.
+ *
+ * "log2 domain": running maxima `m` and sums `l` describe  sum_j exp(S_ij) = l * 2^m .
+ */
+#ifndef VLPCLIP_H_
+#define VLPCLIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLPCLIP_VERSION 100
+
+int vlpclip_version(void);
+const char* vlpclip_last_error(void);
+
+/* number of SMs of the current device (grid sizing / workspace sizing) */
+int vlpclip_sm_count(void);
+
+/* bf16 -> fp16 copy (values of unit-norm embeddings are exactly representable but for |x| < 2^-14) */
+int vlpclip_cast_bf16_to_f16(const void* src_bf16, void* dst_f16, size_t n_elems, void* stream);
+
+/* ---- forward: per-row log-sum-exp statistics of  S = scale * X Y^T  ----
+ * X: [n_rows, d] bf16 row-major (row stride ldx elements), Y: [n_cols, d] bf16 (row stride ldy).
+ * Outputs (each [n_rows] fp32): row_m, row_l in the log2 domain, and (optional, may be NULL)
+ * diag[i] = scale * <X_i, Y_{i - diag_shift}> (the positive-pair logit; rows whose partner
+ * column falls outside [0, n_cols) are left untouched).
+ * workspace: vlpclip_lse_workspace_bytes(n_rows, n_cols, d) bytes.
+ * Replaces VisionLanguageModule.py:459 + the log-sum-exp half of :550 (rows) / :551 (columns,
+ * by calling it with X and Y swapped).
+ */
+size_t vlpclip_lse_workspace_bytes(int n_rows, int n_cols, int d);
+int vlpclip_lse_fwd(const void* x_bf16, int ldx, const void* y_bf16, int ldy, int n_rows,
+                    int n_cols, int d, float scale, int diag_shift, float* row_m, float* row_l,
+                    float* diag, void* workspace, size_t workspace_bytes, void* stream);
+
+/* merge `nparts` partial (m, l) statistics laid out [nparts][n] -> lse (natural log) [n];
+ * out_m / out_l (optional) receive the merged log2-domain pair. Used for cross-rank column
+ * statistics after an all-gather of the partials. */
+int vlpclip_lse_merge(const float* part_m, const float* part_l, int nparts, int n, float* lse,
+                      float* out_m, float* out_l, void* stream);
+
+/* out[0] = sum_i (row_lse[i] - diag[i]), out[1] = sum_i (col_lse[i] - diag[i]) over n entries
+ * (fixed-order, run-to-run reproducible). The caller divides by the global batch size
+ * (VisionLanguageModule.py:550-552). */
+int vlpclip_loss_reduce(const float* row_lse, const float* col_lse, const float* diag, int n,
+                        float* out2, void* stream);
+
+/* ---- backward: dX = scale * G Y with G = (P_row + P_col - 2 delta) / (2 n_global) ----
+ * X, Y: fp16 copies of the embeddings ([n_rows, d] / [n_cols, d], row strides ldx / ldy).
+ * lse_x[n_rows], lse_y[n_cols]: natural-log LSE of the rows of S owned by X / by Y.
+ * delta_ij = 1 iff i == j + diag_shift.
+ * dX: [n_rows, d] fp32 (row stride d), overwritten.
+ * dscale (optional, may be NULL): receives sum_ij G_ij <X_i, Y_j> (fp32, one value).
+ * Replaces autograd of VisionLanguageModule.py:459, :550-552.
+ */
+size_t vlpclip_grad_workspace_bytes(int n_rows, int n_cols, int d);
+int vlpclip_grad(const void* x_f16, int ldx, const void* y_f16, int ldy, const float* lse_x,
+                 const float* lse_y, int n_rows, int n_cols, int d, float scale, int diag_shift,
+                 int n_global, float* dx, float* dscale, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* ---- prologue: emb = normalize(feat @ W) (VisionLanguageModule.py:448-453) ----
+ * feat [n, f] fp32, W [f, d] fp32 (x @ W convention, not nn.Linear).
+ * emb_f32 [n, d] fp32 (returned to the caller), emb_bf16 / emb_f16 [n, d] (operands of the
+ * fused loss), inv_norm [n] = 1 / max(||u||, 1e-12).
+ */
+size_t vlpclip_project_workspace_bytes(int n, int f, int d);
+int vlpclip_project_normalize_fwd(const float* feat, const float* w, int n, int f, int d,
+                                  float* emb_f32, void* emb_bf16, void* emb_f16, float* inv_norm,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* du = (dE - E * rowsum(E * dE)) * inv_norm   (backward of F.normalize, :452-453) */
+int vlpclip_normalize_bwd(const float* emb_f32, const float* d_emb, const float* inv_norm, int n,
+                          int d, float* du, void* stream);
+
+/* generic small GEMMs of the projection backward (tf32 tensor cores, fp32 accumulate):
+ *   C[m, n] = A[m, k] @ B[k, n]      (trans_a = 0)
+ *   C[m, n] = A[k, m]^T @ B[k, n]    (trans_a = 1)   -- dW = feat^T du
+ *   trans_b = 1 reads B as [n, k]                    -- dfeat = du W^T
+ */
+int vlpclip_gemm_tf32(const float* a, const float* b, float* c, int m, int n, int k, int trans_a,
+                      int trans_b, void* workspace, size_t workspace_bytes, void* stream);
+size_t vlpclip_gemm_workspace_bytes(int m, int n, int k);
+
+/* ---- retrieval metrics without the M x M matrix (reference :364-439) ----
+ * For every row i of X (bf16 [n_rows, d]): the indices of the k (<= 16) largest <X_i, Y_j>,
+ * ties broken towards the smaller index, sorted by descending similarity.
+ * out_idx: [n_rows, k] int32.
+ */
+size_t vlpclip_topk_workspace_bytes(int n_rows, int n_cols, int d, int k);
+int vlpclip_topk_rows(const void* x_bf16, int ldx, const void* y_bf16, int ldy, int n_rows,
+                      int n_cols, int d, int k, int32_t* out_idx, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLPCLIP_H_ */

@@ -1,0 +1,103 @@
+// common.cuh -- host-side helpers shared by the kernels of the fused contrastive head:
+// thread-local error string, TMA tensor-map construction, launch helpers.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "sm100_ptx.cuh"
+
+namespace vlp {
+
+// ---- error reporting across the C ABI -------------------------------------------------
+inline char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define VLP_CUDA_OK(expr)                                                             \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess)                                                           \
+      return ::vlp::fail(-2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                         __FILE__, __LINE__);                                         \
+  } while (0)
+
+// ---- TMA descriptors --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        p)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Row-major [outer][inner] matrix of `elem_bytes`-wide elements, row stride `ld` elements.
+// Box = {128 B worth of inner elements, box_outer rows}, 128-byte swizzle, OOB reads give 0.
+inline int make_tmap_sw128(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner,
+                           uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(-3, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  if ((reinterpret_cast<uintptr_t>(gptr) & 15) != 0)
+    return fail(-4, "tensor base address must be 16-byte aligned");
+  if ((ld * elem_bytes) % 16 != 0)
+    return fail(-4, "row stride must be a multiple of 16 bytes (got %llu elements of %d B)",
+                (unsigned long long)ld, elem_bytes);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                           : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-5, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+    n = p.multiProcessorCount;
+  }
+  return n;
+}
+
+inline int check_device_sm100() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(-6, "no CUDA device");
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10)
+    return fail(-6, "device compute capability %d.%d is not sm_100 (B200); no fallback path",
+                major, minor);
+  return 0;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+}  // namespace vlp

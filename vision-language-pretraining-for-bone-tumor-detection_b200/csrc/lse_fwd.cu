@@ -1,0 +1,440 @@
+// lse_fwd.cu -- forward statistics of the symmetric InfoNCE head.
+//
+// Computes, for every row i of X, the online (max, sum-exp) pair of  S_ij = scale * <X_i, Y_j>
+// over all rows j of Y, plus the positive-pair logit S_ii, WITHOUT materialising S
+// (reference: VisionLanguageModule.py:459 `logits = (I @ T.T) * logit_scale` and the
+// log-softmax half of F.cross_entropy at :550 / :551).
+//
+// Mapping to the SM (one persistent CTA per SM, 320 threads):
+//   warp 0      TMA producer: streams Y as [128 rows x 64 k] bf16 boxes (SW128) through an
+//               8-deep smem ring (16 KB per stage).
+//   warp 1      tcgen05 issuer: S[128 x 128] (fp32, TMEM, double buffered) = X * Y_tile^T with the
+//               A operand (X row block, bf16 packed) RESIDENT IN TMEM (TS form: 74 cycles per
+//               K=16 step instead of 107 for the SS form -- see profiles/r01_probe_notes.md).
+//   warps 2..9  softmax: thread = (row, 64-column half); tcgen05.ld the S row, online max/sum in
+//               the log2 domain, one ex2 per logit.
+// Work item = (row block, chunk of column tiles); partial (m, l) pairs per (chunk, half) go to
+// a workspace and are merged by lse_merge_kernel in fixed order (bit reproducible).
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "../../include/vlpclip.h"
+
+namespace vlp {
+
+constexpr int FWD_STAGES = 8;
+constexpr int FWD_STAGE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+constexpr int FWD_THREADS = 320;
+constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: up to 256 columns (d <= 512)
+constexpr uint32_t TMEM_S_COL = 256;    // two S buffers of 128 columns
+
+struct LseParams {
+  const __nv_bfloat16* x;
+  int ldx;
+  int n_rows, n_cols, d;
+  int kblocks;          // ceil(d / 64)
+  int total_tiles;      // ceil(n_cols / 128)
+  int tiles_per_chunk;
+  int n_chunks;
+  int n_row_blocks;
+  int diag_shift;       // delta_ij = 1 iff i == j + diag_shift
+  float scale;          // s
+  float scale_log2;     // s * log2(e)
+  float* part_m;        // [n_chunks * 2][n_rows]
+  float* part_l;
+  float* diag;          // [n_rows] or nullptr
+};
+
+struct FwdBarriers {
+  uint64_t full[FWD_STAGES];
+  uint64_t empty[FWD_STAGES];
+  uint64_t s_full[2];
+  uint64_t s_empty[2];
+  uint64_t x_ready;
+  uint64_t x_free;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(smem + FWD_STAGES * FWD_STAGE_BYTES);
+  const uint32_t ring = smem_u32(smem);
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FWD_STAGES; ++i) {
+      mbar_init(smem_u32(&bars->full[i]), 1);
+      mbar_init(smem_u32(&bars->empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->s_full[i]), 1);
+      mbar_init(smem_u32(&bars->s_empty[i]), 8);  // one arrive per softmax warp
+    }
+    mbar_init(smem_u32(&bars->x_ready), 8);
+    mbar_init(smem_u32(&bars->x_free), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(smem_u32(&bars->tmem_base), 512);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_y);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  const int n_items = p.n_row_blocks * p.n_chunks;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;  // running stage counter
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item / p.n_row_blocks;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            const uint32_t st = it % FWD_STAGES;
+            const uint32_t ph = (it / FWD_STAGES) & 1;
+            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+            mbar_expect_tx(smem_u32(&bars->full[st]), FWD_STAGE_BYTES);
+            tma_load_2d(ring + st * FWD_STAGE_BYTES, &map_y, smem_u32(&bars->full[st]), kb * 64,
+                        t * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, MAJOR_K, MAJOR_K, 128, 128);
+      uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
+        const int chunk = item / p.n_row_blocks;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+        tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++tile_ctr) {
+          const uint32_t buf = tile_ctr & 1;
+          mbar_wait(smem_u32(&bars->s_empty[buf]), ((tile_ctr >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem + TMEM_S_COL + buf * 128;
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            const uint32_t st = it % FWD_STAGES;
+            const uint32_t ph = (it / FWD_STAGES) & 1;
+            mbar_wait(smem_u32(&bars->full[st]), ph);
+            tc_fence_after();
+            const uint32_t sb = ring + st * FWD_STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_ts<1>(d_tmem, tmem + TMEM_X_COL + kb * 32 + ks * 8,
+                         make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | ks) != 0);
+            }
+            umma_commit<1>(smem_u32(&bars->empty[st]));
+          }
+          umma_commit<1>(smem_u32(&bars->s_full[buf]));
+        }
+        umma_commit<1>(smem_u32(&bars->x_free));
+      }
+      // do not exit with an arrive still in flight
+      if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+    }
+  } else {
+    // ================= softmax warps =================
+    const uint32_t quarter = warp & 3;           // TMEM lane quarter this warp may touch
+    const uint32_t half = (warp - 2) >> 2;       // which 64-column half of the tile
+    const uint32_t row_in_blk = quarter * 32 + lane;
+    const uint32_t lane_addr = (quarter * 32u) << 16;
+    const int dp = p.kblocks * 64;               // padded K
+    uint32_t tile_ctr = 0, item_ctr = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
+      const int chunk = item / p.n_row_blocks;
+      const int rb = item % p.n_row_blocks;
+      const int t0 = chunk * p.tiles_per_chunk;
+      const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      const int row = rb * 128 + row_in_blk;
+      const bool row_ok = row < p.n_rows;
+
+      // ---- stage the X row block into TMEM (bf16 pairs packed per 32-bit column) ----
+      if (item_ctr > 0) {
+        mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+        tc_fence_after();
+      }
+      {
+        const int k_begin = half * (dp / 2);
+        const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)(row_ok ? row : 0) * p.ldx);
+        for (int c0 = 0; c0 < dp / 4; c0 += 16) {
+          uint32_t v[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k = k_begin + c0 * 2 + q * 8;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (row_ok && k < p.d) w = __ldg(src + (k >> 3));
+            v[q * 4 + 0] = w.x;
+            v[q * 4 + 1] = w.y;
+            v[q * 4 + 2] = w.z;
+            v[q * 4 + 3] = w.w;
+          }
+          tmem_st_x16(tmem + lane_addr + TMEM_X_COL + k_begin / 2 + c0, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
+      }
+
+      float m_run = -INFINITY, l_run = 0.f;
+      const int dcol = row - p.diag_shift;  // column holding this row's positive pair
+      for (int t = t0; t < t1; ++t, ++tile_ctr) {
+        const uint32_t buf = tile_ctr & 1;
+        mbar_wait(smem_u32(&bars->s_full[buf]), (tile_ctr >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[64];
+        {
+          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+          uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+          const uint32_t a = tmem + lane_addr + TMEM_S_COL + buf * 128 + half * 64;
+          tmem_ld_x32(a, v0);
+          tmem_ld_x32(a + 32, v1);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
+
+        const int col0 = t * 128 + half * 64;
+        // columns past n_cols were zero-filled by TMA: mask them out of the statistics
+        if (col0 + 64 > p.n_cols) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (col0 + j >= p.n_cols) v[j] = __float_as_uint(-INFINITY);
+        }
+        if (p.diag != nullptr && row_ok && dcol >= col0 && dcol < col0 + 64) {
+          float dv = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (col0 + j == dcol) dv = __uint_as_float(v[j]);
+          p.diag[row] = dv * p.scale;
+        }
+        float mx = __uint_as_float(v[0]);
+#pragma unroll
+        for (int j = 1; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        const float m_new = fmaxf(m_run, mx * p.scale_log2);
+        if (m_new != -INFINITY) {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; j += 2) {
+            s0 += ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -m_new));
+            s1 += ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new));
+          }
+          l_run = l_run * ex2_approx(m_run - m_new) + (s0 + s1);
+          m_run = m_new;
+        }
+      }
+      if (row_ok) {
+        const size_t o = (size_t)(chunk * 2 + half) * p.n_rows + row;
+        p.part_m[o] = m_run;
+        p.part_l[o] = l_run;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem, 512);
+}
+
+// merge [nparts][n] partial (m, l) pairs in fixed order
+__global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                                 int nparts, int n, float* __restrict__ lse,
+                                 float* __restrict__ out_m, float* __restrict__ out_l) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float m = -INFINITY;
+  for (int q = 0; q < nparts; ++q) m = fmaxf(m, part_m[(size_t)q * n + i]);
+  float l = 0.f;
+  if (m != -INFINITY) {
+    for (int q = 0; q < nparts; ++q) {
+      const float mq = part_m[(size_t)q * n + i];
+      if (mq != -INFINITY) l += part_l[(size_t)q * n + i] * exp2f(mq - m);
+    }
+  }
+  if (out_m) out_m[i] = m;
+  if (out_l) out_l[i] = l;
+  if (lse) lse[i] = (m + log2f(l)) * kLn2;
+}
+
+// out[0] = sum(row_lse - diag), out[1] = sum(col_lse - diag); single block, fixed order
+__global__ void loss_reduce_kernel(const float* __restrict__ row_lse,
+                                   const float* __restrict__ col_lse,
+                                   const float* __restrict__ diag, int n,
+                                   float* __restrict__ out2) {
+  __shared__ double sh[2][1024];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double dg = diag[i];
+    if (row_lse) a += (double)row_lse[i] - dg;
+    if (col_lse) b += (double)col_lse[i] - dg;
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out2[0] = (float)sh[0][0];
+    out2[1] = (float)sh[1][0];
+  }
+}
+
+__global__ void cast_bf16_to_f16_kernel(const __nv_bfloat16* __restrict__ src,
+                                        __half* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = __float2half_rn(__bfloat162float(src[i]));
+}
+
+// ---- chunking policy: items = row_blocks * chunks should fill whole waves of SMs ----
+static void pick_chunks(int n_row_blocks, int total_tiles, int n_sm, int* n_chunks,
+                        int* tiles_per_chunk) {
+  int best_c = 1;
+  double best_eff = -1.0;
+  const int max_c = total_tiles < 64 ? total_tiles : 64;
+  for (int c = 1; c <= max_c; ++c) {
+    const int tpc = (total_tiles + c - 1) / c;
+    const int cc = (total_tiles + tpc - 1) / tpc;  // non-empty chunks
+    if (cc != c) continue;
+    const long items = (long)n_row_blocks * cc;
+    const long waves = (items + n_sm - 1) / n_sm;
+    // per-item fixed cost (X staging) ~ 1.5 tiles worth
+    const double eff = (double)items * tpc / ((double)waves * n_sm * (tpc + 1.5));
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best_c = cc;
+    }
+  }
+  *n_chunks = best_c;
+  *tiles_per_chunk = (total_tiles + best_c - 1) / best_c;
+  *n_chunks = (total_tiles + *tiles_per_chunk - 1) / *tiles_per_chunk;
+}
+
+static size_t lse_ws_bytes(int n_rows, int n_cols) {
+  const int total_tiles = (n_cols + 127) / 128;
+  const int max_chunks = total_tiles < 64 ? total_tiles : 64;
+  return (size_t)2 * (size_t)(max_chunks * 2) * (size_t)n_rows * sizeof(float);
+}
+
+}  // namespace vlp
+
+using namespace vlp;
+
+extern "C" {
+
+int vlpclip_version(void) { return VLPCLIP_VERSION; }
+const char* vlpclip_last_error(void) { return err_buf(); }
+int vlpclip_sm_count(void) { return sm_count(); }
+
+int vlpclip_cast_bf16_to_f16(const void* src, void* dst, size_t n, void* stream) {
+  if (n == 0) return 0;
+  if (!src || !dst) return fail(-1, "cast: null pointer");
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cast_bf16_to_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)src, (__half*)dst, n);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+size_t vlpclip_lse_workspace_bytes(int n_rows, int n_cols, int d) {
+  (void)d;
+  if (n_rows <= 0 || n_cols <= 0) return 0;
+  return lse_ws_bytes(n_rows, n_cols);
+}
+
+int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols, int d,
+                    float scale, int diag_shift, float* row_m, float* row_l, float* diag,
+                    void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_rows <= 0 || n_cols <= 0) return fail(-1, "lse_fwd: empty problem (%d x %d)", n_rows, n_cols);
+  if (!x || !y || !row_m || !row_l || !workspace) return fail(-1, "lse_fwd: null pointer");
+  if (d <= 0 || d % 8 != 0 || d > 512)
+    return fail(-1, "lse_fwd: embedding dim %d unsupported (need a multiple of 8, <= 512)", d);
+  if (ldx % 8 != 0 || ldy % 8 != 0)
+    return fail(-1, "lse_fwd: row strides must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0)
+    return fail(-1, "lse_fwd: X must be 16-byte aligned");
+  if (!(scale > 0.f)) return fail(-1, "lse_fwd: scale must be positive");
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  if (workspace_bytes < lse_ws_bytes(n_rows, n_cols))
+    return fail(-1, "lse_fwd: workspace too small (%zu < %zu)", workspace_bytes,
+                lse_ws_bytes(n_rows, n_cols));
+
+  LseParams p;
+  p.x = (const __nv_bfloat16*)x;
+  p.ldx = ldx;
+  p.n_rows = n_rows;
+  p.n_cols = n_cols;
+  p.d = d;
+  p.kblocks = (d + 63) / 64;
+  p.total_tiles = (n_cols + 127) / 128;
+  p.n_row_blocks = (n_rows + 127) / 128;
+  const int nsm = sm_count();
+  pick_chunks(p.n_row_blocks, p.total_tiles, nsm, &p.n_chunks, &p.tiles_per_chunk);
+  p.diag_shift = diag_shift;
+  p.scale = scale;
+  p.scale_log2 = scale * kLog2e;
+  const int nparts = p.n_chunks * 2;
+  p.part_m = (float*)workspace;
+  p.part_l = p.part_m + (size_t)nparts * n_rows;
+  p.diag = diag;
+
+  CUtensorMap map_y;
+  rc = make_tmap_sw128(&map_y, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
+  if (rc) return rc;
+
+  const size_t smem = FWD_STAGES * FWD_STAGE_BYTES + sizeof(FwdBarriers) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    attr_set = true;
+  }
+  const int n_items = p.n_row_blocks * p.n_chunks;
+  const int grid = n_items < nsm ? n_items : nsm;
+  lse_partial_kernel<<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+  VLP_CUDA_OK(cudaGetLastError());
+  lse_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_m, p.part_l, nparts, n_rows,
+                                                             nullptr, row_m, row_l);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int vlpclip_lse_merge(const float* part_m, const float* part_l, int nparts, int n, float* lse,
+                      float* out_m, float* out_l, void* stream) {
+  if (n <= 0 || nparts <= 0) return fail(-1, "lse_merge: empty input");
+  if (!part_m || !part_l) return fail(-1, "lse_merge: null pointer");
+  lse_merge_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part_m, part_l, nparts, n,
+                                                                     lse, out_m, out_l);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int vlpclip_loss_reduce(const float* row_lse, const float* col_lse, const float* diag, int n,
+                        float* out2, void* stream) {
+  if (n <= 0) return fail(-1, "loss_reduce: empty input");
+  if (!diag || !out2) return fail(-1, "loss_reduce: null pointer");
+  loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_lse, col_lse, diag, n, out2);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
