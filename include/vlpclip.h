@@ -41,43 +41,56 @@ int vlpclip_cast_bf16_to_f16(const void* src_bf16, void* dst_f16, size_t n_elems
 
 /* ---- forward: per-row log-sum-exp statistics of  S = scale * X Y^T  ----
  * X: [n_rows, d] bf16 row-major (row stride ldx elements), Y: [n_cols, d] bf16 (row stride ldy).
- * Outputs (each [n_rows] fp32): row_m, row_l in the log2 domain, and (optional, may be NULL)
- * diag[i] = scale * <X_i, Y_{i - diag_shift}> (the positive-pair logit; rows whose partner
- * column falls outside [0, n_cols) are left untouched).
+ * The positive pair of row i is column i - diag_shift (if inside [0, n_cols)).
+ * Outputs (each [n_rows] fp32):
+ *   row_max[i] = max_j <X_i, Y_j>                       (raw cosine, NOT scaled, positive included)
+ *   row_l[i]   = sum_{j != positive} exp(scale*<X_i,Y_j>) / 2^fl(k*row_max[i]),  k = scale*log2(e)
+ *   diag[i]    = <X_i, Y_{i - diag_shift}>  (rows without a partner column are left untouched)
+ * (max, l) pairs from different column ranges / ranks are combined with vlpclip_lse_merge.
  * workspace: vlpclip_lse_workspace_bytes(n_rows, n_cols, d) bytes.
  * Replaces VisionLanguageModule.py:459 + the log-sum-exp half of :550 (rows) / :551 (columns,
  * by calling it with X and Y swapped).
  */
 size_t vlpclip_lse_workspace_bytes(int n_rows, int n_cols, int d);
 int vlpclip_lse_fwd(const void* x_bf16, int ldx, const void* y_bf16, int ldy, int n_rows,
-                    int n_cols, int d, float scale, int diag_shift, float* row_m, float* row_l,
+                    int n_cols, int d, float scale, int diag_shift, float* row_max, float* row_l,
                     float* diag, void* workspace, size_t workspace_bytes, void* stream);
 
-/* merge `nparts` partial (m, l) statistics laid out [nparts][n] -> lse (natural log) [n];
- * out_m / out_l (optional) receive the merged log2-domain pair. Used for cross-rank column
- * statistics after an all-gather of the partials. */
-int vlpclip_lse_merge(const float* part_m, const float* part_l, int nparts, int n, float* lse,
-                      float* out_m, float* out_l, void* stream);
+/* merge `nparts` partial (max, l) pairs laid out [nparts][n] (fixed order) and fold the positive
+ * pair logits `diag` [n] (may be NULL = no positive pair) back in.  Any output may be NULL:
+ *   lse      natural-log LSE of the full row
+ *   out_max / out_l   merged pair
+ *   out_lg2l log2(sum_j exp(S_ij)) - k*max   (the form the backward consumes)
+ *   out_q    1 - softmax probability of the positive pair
+ *   out_loss lse - scale*diag  (per-row cross-entropy, log1p-accurate when the positive dominates;
+ *            requires diag) */
+int vlpclip_lse_merge(const float* part_max, const float* part_l, const float* diag, int nparts,
+                      int n, float scale, float* lse, float* out_max, float* out_l, float* out_lg2l,
+                      float* out_q, float* out_loss, void* stream);
 
-/* out[0] = sum_i (row_lse[i] - diag[i]), out[1] = sum_i (col_lse[i] - diag[i]) over n entries
- * (fixed-order, run-to-run reproducible). The caller divides by the global batch size
+/* out2[0] = sum_i row_loss[i], out2[1] = sum_i col_loss[i] over n entries (either may be NULL);
+ * single block, fixed order (reproducible). The caller divides by the global batch size
  * (VisionLanguageModule.py:550-552). */
-int vlpclip_loss_reduce(const float* row_lse, const float* col_lse, const float* diag, int n,
-                        float* out2, void* stream);
+int vlpclip_loss_reduce(const float* row_loss, const float* col_loss, int n, float* out2,
+                        void* stream);
 
-/* ---- backward: dX = scale * G Y with G = (P_row + P_col - 2 delta) / (2 n_global) ----
+/* ---- backward: dX = scale * G Y,
+ *      G = (w_row P_row + w_col P_col - (w_row + w_col) delta) / (2 n_global) ----
+ * (w_row = w_col = 1 is the symmetric loss of :552; other non-negative weights serve callers
+ *  that back-propagate image_loss / text_loss separately.)
  * X, Y: fp16 copies of the embeddings ([n_rows, d] / [n_cols, d], row strides ldx / ldy).
- * lse_x[n_rows], lse_y[n_cols]: natural-log LSE of the rows of S owned by X / by Y.
- * delta_ij = 1 iff i == j + diag_shift.
+ * (x_max, x_lg2l, x_q)[n_rows], (y_max, y_lg2l, y_q)[n_cols]: merged statistics
+ * (vlpclip_lse_merge) of the rows of S owned by X / by Y.  delta_ij = 1 iff i == j + diag_shift.
  * dX: [n_rows, d] fp32 (row stride d), overwritten.
  * dscale (optional, may be NULL): receives sum_ij G_ij <X_i, Y_j> (fp32, one value).
  * Replaces autograd of VisionLanguageModule.py:459, :550-552.
  */
 size_t vlpclip_grad_workspace_bytes(int n_rows, int n_cols, int d);
-int vlpclip_grad(const void* x_f16, int ldx, const void* y_f16, int ldy, const float* lse_x,
-                 const float* lse_y, int n_rows, int n_cols, int d, float scale, int diag_shift,
-                 int n_global, float* dx, float* dscale, void* workspace, size_t workspace_bytes,
-                 void* stream);
+int vlpclip_grad(const void* x_f16, int ldx, const void* y_f16, int ldy, const float* x_max,
+                 const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
+                 const float* y_q, int n_rows, int n_cols, int d, float scale, int diag_shift,
+                 int n_global, float w_row, float w_col, float* dx, float* dscale, void* workspace,
+                 size_t workspace_bytes, void* stream);
 
 /* ---- prologue: emb = normalize(feat @ W) (VisionLanguageModule.py:448-453) ----
  * feat [n, f] fp32, W [f, d] fp32 (x @ W convention, not nn.Linear).

@@ -1,0 +1,604 @@
+// grad_bwd.cu -- backward of the symmetric InfoNCE head by tile recompute.
+//
+//   dX = scale * G Y,   G_ij = (exp(S_ij - lse_x_i) + exp(S_ij - lse_y_j) - 2 delta_ij) / (2 N)
+//   dscale = sum_ij G_ij <X_i, Y_j>
+// (closed form of autograd through VisionLanguageModule.py:459 and :550-552; called once with
+// (X, Y) = (I, T) for dI and once with (T, I) for dT -- G is symmetric under the swap.)
+//
+// A 128-row block of dX in fp32 is 128 x 512 x 4 B = the whole 256 KB tensor memory of one SM, so the
+// S tile and the accumulator cannot share an SM at d = 512. The kernel therefore runs on CTA PAIRS
+// (cluster of 2, one CTA per SM):
+//   rank 0 "producer":  S tile = X Y_t^T with X resident in TMEM (TS form), 8 softmax warps turn
+//                       it into the fp16 tile G*2^13 (two ex2 per logit), staged in local smem
+//                       (K-major, 128B swizzle) and pushed to the peer with one
+//                       cp.async.bulk shared::cta -> shared::cluster (18 B/cycle measured).
+//   rank 1 "consumer":  dX block [128 x d] fp32 stays in TMEM for the whole sweep;
+//                       acc += G_tile (A, smem, K-major) * Y_t (B, smem, MN-major), N = 256 per
+//                       instruction; slot release back to the producer by a multicast
+//                       tcgen05.commit. Epilogue scales and stores (or red.adds when the column
+//                       range is split across clusters).
+// Neither S nor G ever leaves the SM pair.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "../../include/vlpclip.h"
+
+namespace vlp {
+
+constexpr int BWD_THREADS = 320;
+constexpr int P_STAGES = 8;                 // producer ring: [128 q x 64 k] fp16 = 16 KB
+constexpr int P_STAGE_BYTES = 16384;
+constexpr int C_STAGES = 4;                 // consumer ring: [64 q x 256 d] fp16 = 32 KB
+constexpr int C_STAGE_BYTES = 32768;
+constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
+constexpr int G_SLOT_BYTES = 32768;         // [128 rows x 128 q] fp16
+constexpr int G_SLOTS = 2;
+constexpr uint32_t BWD_TMEM_X = 0;          // producer: X block (fp16 packed) cols [0,256)
+constexpr uint32_t BWD_TMEM_S = 256;        // producer: two S buffers
+constexpr float G_SCALE = 8192.f;           // 2^13: keeps softmax tails out of fp16 subnormals
+
+struct GradParams {
+  const __half* x;
+  int ldx;
+  const float* xmax;    // [n_row_blocks*128] raw row max of X rows (0 padded)
+  const float* xlg;     // [n_row_blocks*128] log2(sum) - k*max of X rows (+inf padded)
+  const float* ymax;    // [total_tiles*128]  same for the rows of Y
+  const float* ylg;
+  const float* xq;      // [n_rows] 1 - P_row(positive)   (unpadded, read only on the diagonal)
+  const float* yq;      // [n_cols] 1 - P_col(positive)
+  float w_row, w_col;
+  int n_rows, n_cols, d;
+  int kblocks, total_tiles, tiles_per_chunk, n_chunks, n_row_blocks;
+  int diag_shift;
+  float scale_log2;
+  float out_scale;      // scale / (2 n_global) / 2^13
+  float* dx;            // [n_rows, d]
+  int use_atomics;      // n_chunks > 1
+  float* ds_part;       // [n_items * 8] or nullptr
+};
+
+struct BwdBarriers {
+  uint64_t full[P_STAGES];
+  uint64_t empty[P_STAGES];
+  uint64_t s_full[2];
+  uint64_t s_empty[2];
+  uint64_t x_ready;
+  uint64_t x_free;
+  uint64_t g_full[G_SLOTS];   // lives in the consumer, armed remotely by the producer
+  uint64_t g_empty[G_SLOTS];  // lives in the producer, arrived by the consumer's commit
+  uint64_t acc_full;
+  uint64_t acc_free;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// P_row = 2^(k (s - xmax_i) - xlg_i),  P_col = 2^(k (s - ymax_j) - ylg_j): subtracting the raw
+// maxima first keeps probabilities near 1 (dominant positive pair) accurate to ~1e-7.
+template <bool kDiag>
+__device__ __forceinline__ void softmax_tile(const uint32_t (&v)[64],
+                                             const float4* __restrict__ ymax4,
+                                             const float4* __restrict__ ylg4, float xmax, float xlg,
+                                             float scale_log2, float diag_val, int diag_j,
+                                             uint32_t (&out)[32], float& ds_acc) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float4 ym = __ldg(ymax4 + q);
+    const float4 yl = __ldg(ylg4 + q);
+    const float ymv[4] = {ym.x, ym.y, ym.z, ym.w};
+    const float ylv[4] = {yl.x, yl.y, yl.z, yl.w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q * 4 + e;
+      const float s = __uint_as_float(v[j]);
+      const float a = ex2_approx(fmaf(s - xmax, scale_log2, -xlg));
+      const float b = ex2_approx(fmaf(s - ymv[e], scale_log2, -ylv[e]));
+      float gg = a + b;
+      if (kDiag) gg = (j == diag_j) ? diag_val : gg;  // = -(w_r (1-P_row) + w_c (1-P_col))
+      ds_acc = fmaf(gg, s, ds_acc);
+      g[e] = gg * G_SCALE;
+    }
+    out[q * 2 + 0] = pack_f16x2(g[0], g[1]);
+    out[q * 2 + 1] = pack_f16x2(g[2], g[3]);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BWD_THREADS, 1)
+grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 128 q}
+                 const __grid_constant__ CUtensorMap map_y_mn,  // box {64 d, 64 q}
+                 const GradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  BwdBarriers* bars =
+      reinterpret_cast<BwdBarriers*>(smem + RING_BYTES + G_SLOTS * G_SLOT_BYTES);
+  const uint32_t ring = smem_u32(smem);
+  const uint32_t gslots = ring + RING_BYTES;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P_STAGES; ++i) {
+      mbar_init(smem_u32(&bars->full[i]), 1);
+      mbar_init(smem_u32(&bars->empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->s_full[i]), 1);
+      mbar_init(smem_u32(&bars->s_empty[i]), 8);
+      mbar_init(smem_u32(&bars->g_full[i]), 1);
+      mbar_init(smem_u32(&bars->g_empty[i]), 1);
+    }
+    mbar_init(smem_u32(&bars->x_ready), 8);
+    mbar_init(smem_u32(&bars->x_free), 1);
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    mbar_init(smem_u32(&bars->acc_free), 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(smem_u32(&bars->tmem_base), 512);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_y_k);
+    tma_prefetch_desc(&map_y_mn);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const int n_items = p.n_row_blocks * p.n_chunks;
+
+  if (rank == 0) {
+    // =====================================================================================
+    // producer CTA: S tiles + softmax -> G tiles pushed to the peer
+    // =====================================================================================
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+          const int chunk = item / p.n_row_blocks;
+          const int t0 = chunk * p.tiles_per_chunk;
+          const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+          for (int t = t0; t < t1; ++t)
+            for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+              const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
+              mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+              mbar_expect_tx(smem_u32(&bars->full[st]), P_STAGE_BYTES);
+              tma_load_2d(ring + st * P_STAGE_BYTES, &map_y_k, smem_u32(&bars->full[st]), kb * 64,
+                          t * 128);
+            }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_K, 128, 128);
+        uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
+          const int chunk = item / p.n_row_blocks;
+          const int t0 = chunk * p.tiles_per_chunk;
+          const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+          mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+          tc_fence_after();
+          for (int t = t0; t < t1; ++t, ++tile_ctr) {
+            const uint32_t buf = tile_ctr & 1;
+            mbar_wait(smem_u32(&bars->s_empty[buf]), ((tile_ctr >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem + BWD_TMEM_S + buf * 128;
+            for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+              const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
+              mbar_wait(smem_u32(&bars->full[st]), ph);
+              tc_fence_after();
+              const uint32_t sb = ring + st * P_STAGE_BYTES;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ts<1>(d_tmem, tmem + BWD_TMEM_X + kb * 32 + ks * 8,
+                           make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | ks) != 0);
+              umma_commit<1>(smem_u32(&bars->empty[st]));
+            }
+            umma_commit<1>(smem_u32(&bars->s_full[buf]));
+          }
+          umma_commit<1>(smem_u32(&bars->x_free));
+        }
+        if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+      }
+    } else {
+      // ---- softmax warps ----
+      const uint32_t quarter = warp & 3;
+      const uint32_t half = (warp - 2) >> 2;
+      const uint32_t row_in_blk = quarter * 32 + lane;
+      const uint32_t lane_addr = (quarter * 32u) << 16;
+      const int dp = p.kblocks * 64;
+      const uint32_t sw = row_in_blk & 7;
+      uint32_t tile_ctr = 0, item_ctr = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
+        const int chunk = item / p.n_row_blocks;
+        const int rb = item % p.n_row_blocks;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        const int row = rb * 128 + row_in_blk;
+        const bool row_ok = row < p.n_rows;
+        if (item_ctr > 0) {
+          mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+          tc_fence_after();
+        }
+        {
+          const int k_begin = half * (dp / 2);
+          const uint4* src =
+              reinterpret_cast<const uint4*>(p.x + (size_t)(row_ok ? row : 0) * p.ldx);
+          for (int c0 = 0; c0 < dp / 4; c0 += 16) {
+            uint32_t v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int k = k_begin + c0 * 2 + q * 8;
+              uint4 w = make_uint4(0, 0, 0, 0);
+              if (row_ok && k < p.d) w = __ldg(src + (k >> 3));
+              v[q * 4 + 0] = w.x;
+              v[q * 4 + 1] = w.y;
+              v[q * 4 + 2] = w.z;
+              v[q * 4 + 3] = w.w;
+            }
+            tmem_st_x16(tmem + lane_addr + BWD_TMEM_X + k_begin / 2 + c0, v);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
+        }
+        const float xmax = p.xmax[row];  // padded to n_row_blocks*128
+        const float xlg = p.xlg[row];
+        const int dcol = row_ok ? row - p.diag_shift : -1000000000;
+        float ds_acc = 0.f;
+
+        for (int t = t0; t < t1; ++t, ++tile_ctr) {
+          const uint32_t buf = tile_ctr & 1;
+          mbar_wait(smem_u32(&bars->s_full[buf]), (tile_ctr >> 1) & 1);
+          tc_fence_after();
+          uint32_t v[64];
+          {
+            uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+            const uint32_t a = tmem + lane_addr + BWD_TMEM_S + buf * 128 + half * 64;
+            tmem_ld_x32(a, v0);
+            tmem_ld_x32(a + 32, v1);
+            tmem_ld_wait();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
+
+          const int col0 = t * 128 + half * 64;
+          const float4* ymax4 = reinterpret_cast<const float4*>(p.ymax + col0);
+          const float4* ylg4 = reinterpret_cast<const float4*>(p.ylg + col0);
+          uint32_t out[32];
+          const int diag_j = dcol - col0;
+          const bool has_diag = diag_j >= 0 && diag_j < 64;
+          if (__any_sync(0xffffffffu, has_diag)) {
+            float diag_val = 0.f;
+            if (has_diag) diag_val = -(p.w_row * p.xq[row] + p.w_col * p.yq[dcol]);
+            softmax_tile<true>(v, ymax4, ylg4, xmax, xlg, p.scale_log2, diag_val, diag_j, out,
+                               ds_acc);
+          } else {
+            softmax_tile<false>(v, ymax4, ylg4, xmax, xlg, p.scale_log2, 0.f, diag_j, out, ds_acc);
+          }
+
+          // stage the fp16 G tile (K-major, 128B swizzle) and push it to the consumer CTA
+          const uint32_t slot = tile_ctr & 1;
+          if (tile_ctr >= 2)
+            mbar_wait_cluster(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1);
+          const uint32_t dst = gslots + slot * G_SLOT_BYTES + half * 16384 + row_in_blk * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t a = dst + ((c ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(out[c * 4 + 0]),
+                         "r"(out[c * 4 + 1]), "r"(out[c * 4 + 2]), "r"(out[c * 4 + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          bar_sync(1, 256);
+          if (warp == 2 && lane == 0) {
+            const uint32_t rbar = mapa_shared(smem_u32(&bars->g_full[slot]), 1);
+            const uint32_t rdst = mapa_shared(gslots + slot * G_SLOT_BYTES, 1);
+            asm volatile(
+                "mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
+                    rbar),
+                "r"(G_SLOT_BYTES)
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], "
+                "%2, [%3];" ::"r"(rdst),
+                "r"(gslots + slot * G_SLOT_BYTES), "r"(G_SLOT_BYTES), "r"(rbar)
+                : "memory");
+          }
+        }
+        if (p.ds_part != nullptr) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ds_acc += __shfl_xor_sync(0xffffffffu, ds_acc, o);
+          if (lane == 0) p.ds_part[(size_t)item * 8 + (warp - 2)] = ds_acc;
+        }
+      }
+      // drain: the consumer must have released every slot we pushed before we may exit
+      for (uint32_t back = 0; back < 2 && back < tile_ctr; ++back) {
+        const uint32_t tc = tile_ctr - 1 - back;
+        mbar_wait_cluster(smem_u32(&bars->g_empty[tc & 1]), (tc >> 1) & 1);
+      }
+    }
+  } else {
+    // =====================================================================================
+    // consumer CTA: dX block accumulates in TMEM over the whole column sweep
+    // =====================================================================================
+    const int n_nc = (p.kblocks + 3) / 4;  // 256-wide accumulator chunks
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters) {
+          const int chunk = item / p.n_row_blocks;
+          const int t0 = chunk * p.tiles_per_chunk;
+          const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+          for (int t = t0; t < t1; ++t)
+            for (int nc = 0; nc < n_nc; ++nc) {
+              const int nb = min(4, p.kblocks - nc * 4);
+              for (int kh = 0; kh < 2; ++kh, ++it) {
+                const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
+                mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+                mbar_expect_tx(smem_u32(&bars->full[st]), nb * 8192);
+                for (int b = 0; b < nb; ++b)
+                  tma_load_2d(ring + st * C_STAGE_BYTES + b * 8192, &map_y_mn,
+                              smem_u32(&bars->full[st]), (nc * 4 + b) * 64, t * 128 + kh * 64);
+              }
+            }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
+          const int chunk = item / p.n_row_blocks;
+          const int t0 = chunk * p.tiles_per_chunk;
+          const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+          if (item_ctr > 0) {
+            mbar_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1);
+            tc_fence_after();
+          }
+          for (int t = t0; t < t1; ++t, ++tile_ctr) {
+            const uint32_t slot = tile_ctr & 1;
+            mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1);
+            tc_fence_after();
+            const uint32_t ga = gslots + slot * G_SLOT_BYTES;
+            for (int nc = 0; nc < n_nc; ++nc) {
+              const int nb = min(4, p.kblocks - nc * 4);
+              const uint32_t idesc =
+                  make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
+              for (int kh = 0; kh < 2; ++kh, ++it) {
+                const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
+                mbar_wait(smem_u32(&bars->full[st]), ph);
+                tc_fence_after();
+                const uint32_t sb = ring + st * C_STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint64_t ad = make_sdesc_sw128(ga + kh * 16384 + i * 32, 0, 1024);
+                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, 8192, 1024);
+                  umma_ss<1>(tmem + nc * 256, ad, bd, idesc, !(t == t0 && kh == 0 && i == 0));
+                }
+                umma_commit<1>(smem_u32(&bars->empty[st]));
+              }
+            }
+            // release the G slot in the producer CTA (rank 0)
+            umma_commit_mcast<1>(smem_u32(&bars->g_empty[slot]), 0x1);
+          }
+          umma_commit<1>(smem_u32(&bars->acc_full));
+        }
+      }
+    } else if (warp < 6) {
+      // ---- epilogue: TMEM accumulator -> global ----
+      const uint32_t quarter = warp & 3;
+      const uint32_t row_in_blk = quarter * 32 + lane;
+      const uint32_t lane_addr = (quarter * 32u) << 16;
+      uint32_t item_ctr = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
+        const int rb = item % p.n_row_blocks;
+        const int row = rb * 128 + row_in_blk;
+        mbar_wait(smem_u32(&bars->acc_full), item_ctr & 1);
+        tc_fence_after();
+        float* orow = p.dx + (size_t)row * p.d;
+        for (int c = 0; c < p.kblocks * 64; c += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(tmem + lane_addr + c, v);
+          tmem_ld_wait();
+          if (row < p.n_rows) {
+            if (p.use_atomics) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c + j < p.d) atomicAdd(orow + c + j, __uint_as_float(v[j]) * p.out_scale);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (c + j < p.d) {
+                  float4 o;
+                  o.x = __uint_as_float(v[j + 0]) * p.out_scale;
+                  o.y = __uint_as_float(v[j + 1]) * p.out_scale;
+                  o.z = __uint_as_float(v[j + 2]) * p.out_scale;
+                  o.w = __uint_as_float(v[j + 3]) * p.out_scale;
+                  *reinterpret_cast<float4*>(orow + c + j) = o;
+                }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_free));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc<1>(tmem, 512);
+}
+
+// pad the per-row statistics to whole tiles: max -> 0, lg2l -> +inf (probability 0)
+// (a direction weight w >= 0 is folded in as lg2l - log2(w): w * 2^e = 2^(e + log2 w))
+__global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __restrict__ lg, int n,
+                                 int n_pad, float log2w, float* __restrict__ mx_out,
+                                 float* __restrict__ lg_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) {
+    mx_out[i] = i < n ? mx[i] : 0.f;
+    lg_out[i] = i < n ? lg[i] - log2w : INFINITY;
+  }
+}
+
+__global__ void ds_reduce_kernel(const float* __restrict__ part, int n, float mul,
+                                 float* __restrict__ out) {
+  __shared__ double sh[256];
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += (double)part[i];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(sh[0] * (double)mul);
+}
+
+static void pick_chunks_pairs(int n_row_blocks, int total_tiles, int n_pairs, int* n_chunks,
+                              int* tiles_per_chunk) {
+  int best_c = 1;
+  double best_eff = -1.0;
+  const int max_c = total_tiles < 16 ? total_tiles : 16;
+  for (int c = 1; c <= max_c; ++c) {
+    const int tpc = (total_tiles + c - 1) / c;
+    const int cc = (total_tiles + tpc - 1) / tpc;
+    if (cc != c) continue;
+    const long items = (long)n_row_blocks * cc;
+    const long waves = (items + n_pairs - 1) / n_pairs;
+    // per-item fixed cost (X staging + accumulator flush) ~ 3 tiles worth
+    double eff = (double)items * tpc / ((double)waves * n_pairs * (tpc + 3.0));
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best_c = cc;
+    }
+  }
+  *tiles_per_chunk = (total_tiles + best_c - 1) / best_c;
+  *n_chunks = (total_tiles + *tiles_per_chunk - 1) / *tiles_per_chunk;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static size_t grad_ws_bytes(int n_rows, int n_cols) {
+  const size_t nrb = (n_rows + 127) / 128, nt = (n_cols + 127) / 128;
+  return 2 * align256(nrb * 128 * 4) + 2 * align256(nt * 128 * 4) + align256(nrb * 16 * 8 * 4) + 256;
+}
+
+}  // namespace vlp
+
+using namespace vlp;
+
+extern "C" {
+
+size_t vlpclip_grad_workspace_bytes(int n_rows, int n_cols, int d) {
+  (void)d;
+  if (n_rows <= 0 || n_cols <= 0) return 0;
+  return grad_ws_bytes(n_rows, n_cols);
+}
+
+int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_max,
+                 const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
+                 const float* y_q, int n_rows,
+                 int n_cols, int d, float scale, int diag_shift, int n_global, float w_row,
+                 float w_col, float* dx, float* dscale, void* workspace, size_t workspace_bytes,
+                 void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_rows <= 0 || n_cols <= 0) return fail(-1, "grad: empty problem (%d x %d)", n_rows, n_cols);
+  if (!x || !y || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q || !dx || !workspace)
+    return fail(-1, "grad: null pointer");
+  if (d <= 0 || d % 8 != 0 || d > 512)
+    return fail(-1, "grad: embedding dim %d unsupported (need a multiple of 8, <= 512)", d);
+  if (ldx % 8 != 0 || ldy % 8 != 0) return fail(-1, "grad: row strides must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(dx) & 15) != 0)
+    return fail(-1, "grad: X and dX must be 16-byte aligned");
+  if (!(scale > 0.f) || n_global <= 0) return fail(-1, "grad: bad scale / n_global");
+  if (!(w_row >= 0.f) || !(w_col >= 0.f) || !(w_row + w_col > 0.f))
+    return fail(-1, "grad: direction weights must be >= 0 and not both zero");
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  if (workspace_bytes < grad_ws_bytes(n_rows, n_cols))
+    return fail(-1, "grad: workspace too small (%zu < %zu)", workspace_bytes,
+                grad_ws_bytes(n_rows, n_cols));
+
+  GradParams p;
+  p.x = (const __half*)x;
+  p.ldx = ldx;
+  p.n_rows = n_rows;
+  p.n_cols = n_cols;
+  p.d = d;
+  p.kblocks = (d + 63) / 64;
+  p.total_tiles = (n_cols + 127) / 128;
+  p.n_row_blocks = (n_rows + 127) / 128;
+  const int n_pairs = sm_count() / 2;
+  pick_chunks_pairs(p.n_row_blocks, p.total_tiles, n_pairs, &p.n_chunks, &p.tiles_per_chunk);
+  p.diag_shift = diag_shift;
+  p.scale_log2 = scale * kLog2e;
+  p.w_row = w_row;
+  p.w_col = w_col;
+  p.xq = x_q;
+  p.yq = y_q;
+  p.out_scale = scale / (2.0f * (float)n_global) / G_SCALE;
+  p.dx = dx;
+  p.use_atomics = p.n_chunks > 1;
+
+  uint8_t* ws = (uint8_t*)workspace;
+  const int npx = p.n_row_blocks * 128, npy = p.total_tiles * 128;
+  float* xmax = (float*)ws;
+  ws += align256((size_t)npx * 4);
+  float* xlg = (float*)ws;
+  ws += align256((size_t)npx * 4);
+  float* ymax = (float*)ws;
+  ws += align256((size_t)npy * 4);
+  float* ylg = (float*)ws;
+  ws += align256((size_t)npy * 4);
+  float* ds_part = (float*)ws;
+  p.xmax = xmax;
+  p.xlg = xlg;
+  p.ymax = ymax;
+  p.ylg = ylg;
+  p.ds_part = dscale ? ds_part : nullptr;
+  stats_pad_kernel<<<(npx + 255) / 256, 256, 0, stream>>>(x_max, x_lg2l, n_rows, npx,
+                                                          log2f(w_row), xmax, xlg);
+  stats_pad_kernel<<<(npy + 255) / 256, 256, 0, stream>>>(y_max, y_lg2l, n_cols, npy,
+                                                          log2f(w_col), ymax, ylg);
+  VLP_CUDA_OK(cudaGetLastError());
+  if (p.use_atomics) VLP_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)n_rows * d * sizeof(float), stream));
+
+  CUtensorMap map_k, map_mn;
+  rc = make_tmap_sw128(&map_k, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
+  if (rc) return rc;
+  rc = make_tmap_sw128(&map_mn, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 64);
+  if (rc) return rc;
+
+  const size_t smem = RING_BYTES + G_SLOTS * G_SLOT_BYTES + sizeof(BwdBarriers) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLP_CUDA_OK(cudaFuncSetAttribute(grad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    attr_set = true;
+  }
+  const int n_items = p.n_row_blocks * p.n_chunks;
+  const int clusters = n_items < n_pairs ? n_items : n_pairs;
+  grad_pair_kernel<<<clusters * 2, BWD_THREADS, smem, stream>>>(map_k, map_mn, p);
+  VLP_CUDA_OK(cudaGetLastError());
+  if (dscale) {
+    ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, n_items * 8, 1.0f / (2.0f * (float)n_global),
+                                            dscale);
+    VLP_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"

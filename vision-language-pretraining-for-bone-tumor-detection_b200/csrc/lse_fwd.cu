@@ -39,9 +39,9 @@ struct LseParams {
   int diag_shift;       // delta_ij = 1 iff i == j + diag_shift
   float scale;          // s
   float scale_log2;     // s * log2(e)
-  float* part_m;        // [n_chunks * 2][n_rows]
+  float* part_m;        // [n_chunks * 2][n_rows] raw (unscaled) running max of <X_i, Y_j>
   float* part_l;
-  float* diag;          // [n_rows] or nullptr
+  float* diag;          // [n_rows]: raw <X_i, Y_{i - diag_shift}>
 };
 
 struct FwdBarriers {
@@ -186,8 +186,9 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
       }
 
-      float m_run = -INFINITY, l_run = 0.f;
-      const int dcol = row - p.diag_shift;  // column holding this row's positive pair
+      float m_run = -INFINITY, mraw_run = -INFINITY, l_run = 0.f;
+      // column holding this row's positive pair (none for padded rows)
+      const int dcol = row_ok ? row - p.diag_shift : -1000000000;
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t buf = tile_ctr & 1;
         mbar_wait(smem_u32(&bars->s_full[buf]), (tile_ctr >> 1) & 1);
@@ -212,18 +213,24 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           for (int j = 0; j < 64; ++j)
             if (col0 + j >= p.n_cols) v[j] = __float_as_uint(-INFINITY);
         }
-        if (p.diag != nullptr && row_ok && dcol >= col0 && dcol < col0 + 64) {
-          float dv = 0.f;
-#pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (col0 + j == dcol) dv = __uint_as_float(v[j]);
-          p.diag[row] = dv * p.scale;
-        }
         float mx = __uint_as_float(v[0]);
 #pragma unroll
         for (int j = 1; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-        const float m_new = fmaxf(m_run, mx * p.scale_log2);
-        if (m_new != -INFINITY) {
+        // positive pair: remember its raw logit, keep it in the running max, but leave it out of
+        // the sum (the merge step adds it back through log1p -> no cancellation for tiny losses)
+        if (__any_sync(0xffffffffu, dcol >= col0 && dcol < col0 + 64)) {
+          float dv = 0.f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (col0 + j == dcol) {
+              dv = __uint_as_float(v[j]);
+              v[j] = __float_as_uint(-INFINITY);
+            }
+          if (row_ok && dcol >= col0 && dcol < col0 + 64) p.diag[row] = dv;
+        }
+        const float mraw_new = fmaxf(mraw_run, mx);
+        const float m_new = mraw_new * p.scale_log2;  // log2-domain reference of this row
+        if (mraw_new != -INFINITY) {
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int j = 0; j < 64; j += 2) {
@@ -232,11 +239,12 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           }
           l_run = l_run * ex2_approx(m_run - m_new) + (s0 + s1);
           m_run = m_new;
+          mraw_run = mraw_new;
         }
       }
       if (row_ok) {
         const size_t o = (size_t)(chunk * 2 + half) * p.n_rows + row;
-        p.part_m[o] = m_run;
+        p.part_m[o] = mraw_run;
         p.part_l[o] = l_run;
       }
     }
@@ -247,37 +255,57 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
 }
 
-// merge [nparts][n] partial (m, l) pairs in fixed order
+// Merge [nparts][n] partial (max, l) pairs in fixed order.
+// A partial means  sum_{j != positive} exp(scale * c_j) = l * 2^fl(k * max)  with
+// k = scale * log2(e), fl() the fp32 product (exactly what the streaming kernel subtracted inside
+// ex2) and max taken over all columns INCLUDING the positive pair.  With t = 2^(k (diag - max)):
+//   out_lg2l = log2(l + t) - k*max   (fl() residual removed with an exact fma)
+//   out_q    = l / (l + t) = 1 - P(positive)
+//   out_loss = ln(sum_j exp(S_ij)) - S_ii = ln2 * (log2(l + t) + k (max - diag)), via log1p when the
+//              positive pair is the row maximum
+// diag == nullptr: no positive pair in these columns (t = 0).
 __global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
-                                 int nparts, int n, float* __restrict__ lse,
-                                 float* __restrict__ out_m, float* __restrict__ out_l) {
+                                 const float* __restrict__ diag, int nparts, int n,
+                                 float scale_log2, float* __restrict__ lse,
+                                 float* __restrict__ out_max, float* __restrict__ out_l,
+                                 float* __restrict__ out_lg2l, float* __restrict__ out_q,
+                                 float* __restrict__ out_loss) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float m = -INFINITY;
   for (int q = 0; q < nparts; ++q) m = fmaxf(m, part_m[(size_t)q * n + i]);
+  const float m2 = m * scale_log2;
   float l = 0.f;
   if (m != -INFINITY) {
     for (int q = 0; q < nparts; ++q) {
       const float mq = part_m[(size_t)q * n + i];
-      if (mq != -INFINITY) l += part_l[(size_t)q * n + i] * exp2f(mq - m);
+      if (mq != -INFINITY) l += part_l[(size_t)q * n + i] * exp2f(mq * scale_log2 - m2);
     }
   }
-  if (out_m) out_m[i] = m;
+  float t = 0.f, gap = 0.f;  // gap = k (max - diag) >= 0
+  if (diag) {
+    gap = scale_log2 * (m - diag[i]);
+    t = exp2f(-gap);
+  }
+  const float tot = l + t;
+  const float lg = (t == 1.0f) ? log1pf(l) * kLog2e : log2f(tot);
+  if (out_max) out_max[i] = m;
   if (out_l) out_l[i] = l;
-  if (lse) lse[i] = (m + log2f(l)) * kLn2;
+  if (out_lg2l) out_lg2l[i] = lg - fmaf(scale_log2, m, -m2);
+  if (out_q) out_q[i] = l / tot;
+  if (out_loss) out_loss[i] = (lg + gap) * kLn2;
+  if (lse) lse[i] = (m2 + lg) * kLn2;
 }
 
-// out[0] = sum(row_lse - diag), out[1] = sum(col_lse - diag); single block, fixed order
-__global__ void loss_reduce_kernel(const float* __restrict__ row_lse,
-                                   const float* __restrict__ col_lse,
-                                   const float* __restrict__ diag, int n,
+// out2[0] = sum(row_loss), out2[1] = sum(col_loss); single block, fixed order => reproducible
+__global__ void loss_reduce_kernel(const float* __restrict__ row_loss,
+                                   const float* __restrict__ col_loss, int n,
                                    float* __restrict__ out2) {
   __shared__ double sh[2][1024];
   double a = 0.0, b = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double dg = diag[i];
-    if (row_lse) a += (double)row_lse[i] - dg;
-    if (col_lse) b += (double)col_lse[i] - dg;
+    if (row_loss) a += (double)row_loss[i];
+    if (col_loss) b += (double)col_loss[i];
   }
   sh[0][threadIdx.x] = a;
   sh[1][threadIdx.x] = b;
@@ -360,11 +388,12 @@ size_t vlpclip_lse_workspace_bytes(int n_rows, int n_cols, int d) {
 }
 
 int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols, int d,
-                    float scale, int diag_shift, float* row_m, float* row_l, float* diag,
+                    float scale, int diag_shift, float* row_max, float* row_l, float* diag,
                     void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "lse_fwd: empty problem (%d x %d)", n_rows, n_cols);
-  if (!x || !y || !row_m || !row_l || !workspace) return fail(-1, "lse_fwd: null pointer");
+  if (!x || !y || !row_max || !row_l || !diag || !workspace)
+    return fail(-1, "lse_fwd: null pointer");
   if (d <= 0 || d % 8 != 0 || d > 512)
     return fail(-1, "lse_fwd: embedding dim %d unsupported (need a multiple of 8, <= 512)", d);
   if (ldx % 8 != 0 || ldy % 8 != 0)
@@ -412,27 +441,31 @@ int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, 
   const int grid = n_items < nsm ? n_items : nsm;
   lse_partial_kernel<<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
   VLP_CUDA_OK(cudaGetLastError());
-  lse_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_m, p.part_l, nparts, n_rows,
-                                                             nullptr, row_m, row_l);
+  lse_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_m, p.part_l, nullptr, nparts,
+                                                             n_rows, p.scale_log2, nullptr, row_max,
+                                                             row_l, nullptr, nullptr, nullptr);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int vlpclip_lse_merge(const float* part_m, const float* part_l, int nparts, int n, float* lse,
-                      float* out_m, float* out_l, void* stream) {
+int vlpclip_lse_merge(const float* part_max, const float* part_l, const float* diag, int nparts,
+                      int n, float scale, float* lse, float* out_max, float* out_l, float* out_lg2l,
+                      float* out_q, float* out_loss, void* stream) {
   if (n <= 0 || nparts <= 0) return fail(-1, "lse_merge: empty input");
-  if (!part_m || !part_l) return fail(-1, "lse_merge: null pointer");
-  lse_merge_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part_m, part_l, nparts, n,
-                                                                     lse, out_m, out_l);
+  if (!part_max || !part_l) return fail(-1, "lse_merge: null pointer");
+  if (out_loss && !diag) return fail(-1, "lse_merge: per-row loss needs the positive-pair logits");
+  lse_merge_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      part_max, part_l, diag, nparts, n, scale * kLog2e, lse, out_max, out_l, out_lg2l, out_q,
+      out_loss);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int vlpclip_loss_reduce(const float* row_lse, const float* col_lse, const float* diag, int n,
-                        float* out2, void* stream) {
+int vlpclip_loss_reduce(const float* row_loss, const float* col_loss, int n, float* out2,
+                        void* stream) {
   if (n <= 0) return fail(-1, "loss_reduce: empty input");
-  if (!diag || !out2) return fail(-1, "loss_reduce: null pointer");
-  loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_lse, col_lse, diag, n, out2);
+  if (!out2) return fail(-1, "loss_reduce: null pointer");
+  loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, col_loss, n, out2);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,423 @@
+"""Functional core of the fused CLIP head (host side, thin Python over the C ABI).
+
+Mirrors the arithmetic of the reference's ``VisionLanguageModule.forward`` (lines 448-459) and
+``_compute_loss`` (lines 533-552) but never builds the N x N logit matrix:
+
+    fused_clip_loss_from_embeddings(I, T, logit_scale)        embedding-level entry (parity surface)
+    fused_clip_loss(f_img, f_txt, W_img, W_txt, logit_scale)  projection + normalise + loss
+    project_normalize(features, W)                            prologue only (returns embeddings)
+
+All compute runs in ``csrc/libvlpclip.so`` (hand-written sm_100a kernels).  Tensors must live on a
+B200; anything else raises -- there is no CPU / eager fallback.  PyTorch only provides memory,
+streams, autograd bookkeeping and (for the sharded variant) ``torch.distributed`` collectives.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+LOGIT_SCALE_MAX = 100.0  # reference: torch.clamp(logit_scale.exp(), max=100)  (:457)
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} lives on {t.device}: the fused CLIP head only runs on a CUDA "
+                           "sm_100 device (no CPU fallback)")
+
+
+def _as_2d_contig(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D [batch, dim], got shape {tuple(t.shape)}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def cast_bf16_to_f16(src: torch.Tensor) -> torch.Tensor:
+    """fp16 copy of bf16 embeddings (operands of the backward GEMMs)."""
+    _require_cuda(src, "src")
+    assert src.dtype == torch.bfloat16 and src.is_contiguous()
+    dst = torch.empty_like(src, dtype=torch.float16)
+    lib = _lib.load()
+    _lib.check(lib.vlpclip_cast_bf16_to_f16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()),
+               "cast_bf16_to_f16")
+    return dst
+
+
+def lse_stats(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shift: int = 0):
+    """Row statistics of ``scale * x @ y.T``: (row_max [n], row_l [n], diag [n]).
+
+    ``row_l`` leaves out the positive pair (column ``i - diag_shift``); ``diag`` holds its raw
+    cosine (0 for rows without a partner column)."""
+    _require_cuda(x_bf16, "x")
+    _require_cuda(y_bf16, "y")
+    if x_bf16.dtype != torch.bfloat16 or y_bf16.dtype != torch.bfloat16:
+        raise ValueError("lse_stats expects bf16 operands")
+    x = _as_2d_contig(x_bf16, "x")
+    y = _as_2d_contig(y_bf16, "y")
+    if x.shape[1] != y.shape[1]:
+        raise ValueError(f"embedding dims differ: {x.shape[1]} vs {y.shape[1]}")
+    n_rows, d = x.shape
+    n_cols = y.shape[0]
+    lib = _lib.load()
+    dev = x.device
+    row_max = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    row_l = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+    nbytes = lib.vlpclip_lse_workspace_bytes(n_rows, n_cols, d)
+    ws = _ws(nbytes, dev)
+    rc = lib.vlpclip_lse_fwd(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows, n_cols, d,
+                             float(scale), int(diag_shift), row_max.data_ptr(), row_l.data_ptr(),
+                             diag.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    _lib.check(rc, "lse_fwd")
+    return row_max, row_l, diag
+
+
+def merge_stats(part_max: torch.Tensor, part_l: torch.Tensor, diag: Optional[torch.Tensor],
+                scale: float, want_lse: bool = False):
+    """Merge [P, n] partial statistics and fold the positive-pair logits back in.
+
+    Returns (max [n], lg2l [n], q [n], row_loss [n] | None, lse [n] | None)."""
+    if part_max.dim() == 1:
+        part_max = part_max.unsqueeze(0)
+        part_l = part_l.unsqueeze(0)
+    part_max = part_max.contiguous()
+    part_l = part_l.contiguous()
+    nparts, n = part_max.shape
+    dev = part_max.device
+    lib = _lib.load()
+    out_max = torch.empty(n, dtype=torch.float32, device=dev)
+    out_lg = torch.empty(n, dtype=torch.float32, device=dev)
+    out_q = torch.empty(n, dtype=torch.float32, device=dev)
+    out_loss = torch.empty(n, dtype=torch.float32, device=dev) if diag is not None else None
+    lse = torch.empty(n, dtype=torch.float32, device=dev) if want_lse else None
+    rc = lib.vlpclip_lse_merge(part_max.data_ptr(), part_l.data_ptr(),
+                               diag.data_ptr() if diag is not None else None, nparts, n,
+                               float(scale), lse.data_ptr() if want_lse else None,
+                               out_max.data_ptr(), None, out_lg.data_ptr(), out_q.data_ptr(),
+                               out_loss.data_ptr() if out_loss is not None else None, _stream())
+    _lib.check(rc, "lse_merge")
+    return out_max, out_lg, out_q, out_loss, lse
+
+
+def _loss_sums(row_loss: torch.Tensor, col_loss: torch.Tensor) -> torch.Tensor:
+    """[sum_i row_loss, sum_i col_loss] as a 2-vector (fp32, device; fixed summation order)."""
+    lib = _lib.load()
+    out2 = torch.empty(2, dtype=torch.float32, device=row_loss.device)
+    rc = lib.vlpclip_loss_reduce(row_loss.data_ptr(), col_loss.data_ptr(), row_loss.numel(),
+                                 out2.data_ptr(), _stream())
+    _lib.check(rc, "loss_reduce")
+    return out2
+
+
+def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_global: int,
+          w_row: float = 1.0, w_col: float = 1.0, want_dscale: bool = False):
+    """x_stats / y_stats = (max, lg2l, q) of the rows of S owned by X / Y."""
+    lib = _lib.load()
+    n_rows, d = x_f16.shape
+    n_cols = y_f16.shape[0]
+    dev = x_f16.device
+    dx = torch.empty(n_rows, d, dtype=torch.float32, device=dev)
+    ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+    nbytes = lib.vlpclip_grad_workspace_bytes(n_rows, n_cols, d)
+    ws = _ws(nbytes, dev)
+    rc = lib.vlpclip_grad(x_f16.data_ptr(), x_f16.stride(0), y_f16.data_ptr(), y_f16.stride(0),
+                          x_stats[0].data_ptr(), x_stats[1].data_ptr(), x_stats[2].data_ptr(),
+                          y_stats[0].data_ptr(), y_stats[1].data_ptr(), y_stats[2].data_ptr(),
+                          n_rows, n_cols, d, float(scale), int(diag_shift), int(n_global),
+                          float(w_row), float(w_col), dx.data_ptr(),
+                          ds.data_ptr() if want_dscale else None, ws.data_ptr(), nbytes, _stream())
+    _lib.check(rc, "grad")
+    return dx, ds
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _group_info(group):
+    if group is None:
+        return 1, 0
+    dist = _dist()
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _all_gather_rows(t: torch.Tensor, group, world: int) -> torch.Tensor:
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    _dist().all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# embedding-level fused loss
+# ----------------------------------------------------------------------------------------------
+class _FusedClipLoss(torch.autograd.Function):
+    """loss, image_loss, text_loss = CLIP loss of (I, T, logit_scale); grads by tile recompute.
+
+    Sharded mode (``group`` given): every rank passes its local rows; negatives are the global
+    batch (all-gather of T, all-gather + merge of the per-column partial statistics, all-reduce of
+    the loss sums; backward: reduce-scatter of dT_all, all-reduce of d logit_scale).
+    """
+
+    @staticmethod
+    def forward(ctx, image_embeddings, text_embeddings, logit_scale, i_bf16, t_bf16, i_f16, t_f16,
+                group, grad_scale):
+        ctx.set_materialize_grads(False)
+        _require_cuda(image_embeddings, "image_embeddings")
+        _require_cuda(text_embeddings, "text_embeddings")
+        if image_embeddings.shape != text_embeddings.shape or image_embeddings.dim() != 2:
+            raise ValueError("image/text embeddings must both be [batch, dim] with equal shapes, got "
+                             f"{tuple(image_embeddings.shape)} and {tuple(text_embeddings.shape)}")
+        if logit_scale.numel() != 1:
+            raise ValueError("logit_scale must have exactly one element (reference shape [1])")
+        n_loc, d = image_embeddings.shape
+        if n_loc == 0:
+            raise ValueError("empty batch")
+        dev = image_embeddings.device
+        world, rank = _group_info(group)
+        n_glob = n_loc * world
+
+        # reference :456-457 -- exp + clamp(max=100); value needed on the host as a launch scalar
+        ls_val = float(logit_scale.detach().double().item())
+        e = math.exp(ls_val)
+        scale = min(e, LOGIT_SCALE_MAX)
+        clamped = e > LOGIT_SCALE_MAX
+
+        if i_bf16 is None:
+            i_bf16 = image_embeddings.detach().to(torch.bfloat16).contiguous()
+        if t_bf16 is None:
+            t_bf16 = text_embeddings.detach().to(torch.bfloat16).contiguous()
+
+        if world > 1:
+            t_all_bf16 = _all_gather_rows(t_bf16, group, world)
+        else:
+            t_all_bf16 = t_bf16
+        shift_rows = -rank * n_loc  # delta_ij = 1 iff i_loc == j_glob - rank*b
+
+        # rows of S owned by the local images: complete after one sweep over T_all
+        r_max_p, r_l_p, r_diag = lse_stats(i_bf16, t_all_bf16, scale, shift_rows)
+        r_max, r_lg, r_q, r_loss, _ = merge_stats(r_max_p, r_l_p, r_diag, scale)
+        # columns (= rows of S^T owned by the texts): partial over the local images
+        lo = rank * n_loc
+        c_max_p, c_l_p, c_diag = lse_stats(t_all_bf16, i_bf16, scale, lo)
+        if world > 1:
+            c_max_p = _all_gather_rows(c_max_p.unsqueeze(0), group, world)
+            c_l_p = _all_gather_rows(c_l_p.unsqueeze(0), group, world)
+            c_diag = _all_gather_rows(c_diag[lo:lo + n_loc], group, world)
+        c_max, c_lg, c_q, c_loss, _ = merge_stats(c_max_p, c_l_p, c_diag, scale)
+        sums = _loss_sums(r_loss, c_loss[lo:lo + n_loc])
+        if world > 1:
+            _dist().all_reduce(sums, group=group)
+        losses = sums / float(n_glob)
+        image_loss = losses[0]
+        text_loss = losses[1]
+        loss = (image_loss + text_loss) * 0.5                      # reference :552
+
+        ctx.group = group
+        ctx.world, ctx.rank = world, rank
+        ctx.n_loc, ctx.n_glob = n_loc, n_glob
+        ctx.scale, ctx.exp_ls, ctx.clamped = scale, e, clamped
+        ctx.grad_scale = float(grad_scale)
+        ctx.in_dtypes = (image_embeddings.dtype, text_embeddings.dtype, logit_scale.dtype)
+        ctx.ls_shape = logit_scale.shape
+        ctx.save_for_backward(i_bf16, t_all_bf16, r_max, r_lg, r_q, c_max, c_lg, c_q)
+        ctx.f16 = (i_f16, t_f16 if world == 1 else None)
+        return loss, image_loss, text_loss
+
+    @staticmethod
+    def backward(ctx, g_loss, g_il, g_tl):
+        i_bf16, t_all_bf16, r_max, r_lg, r_q, c_max, c_lg, c_q = ctx.saved_tensors
+        r_stats, c_stats = (r_max, r_lg, r_q), (c_max, c_lg, c_q)
+        need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if not (need_i or need_t or need_ls) or (g_loss is None and g_il is None and g_tl is None):
+            return (None,) * 9
+        # direction weights: d/dS = (w_r P_row + w_c P_col - (w_r + w_c) delta) / (2N)
+        mul = None
+        if g_il is None and g_tl is None:
+            w_r = w_c = 1.0
+            mul = g_loss                      # device scalar, applied after the kernels
+        else:
+            gl = 0.0 if g_loss is None else float(g_loss.item())
+            w_r = gl + 2.0 * (0.0 if g_il is None else float(g_il.item()))
+            w_c = gl + 2.0 * (0.0 if g_tl is None else float(g_tl.item()))
+            sign = 1.0
+            if w_r < 0 or w_c < 0:
+                if w_r > 0 or w_c > 0:
+                    raise NotImplementedError("mixed-sign upstream gradients for image/text loss")
+                w_r, w_c, sign = -w_r, -w_c, -1.0
+            if w_r == 0.0 and w_c == 0.0:
+                return (None,) * 9
+            mul = torch.tensor(sign, dtype=torch.float32, device=i_bf16.device)
+
+        i_f16, t_f16 = ctx.f16
+        if i_f16 is None:
+            i_f16 = cast_bf16_to_f16(i_bf16)
+        t_all_f16 = t_f16 if t_f16 is not None else cast_bf16_to_f16(t_all_bf16)
+        n_loc, n_glob, rank, world = ctx.n_loc, ctx.n_glob, ctx.rank, ctx.world
+        scale = ctx.scale
+        gs = ctx.grad_scale
+
+        d_i = d_t = d_ls = None
+        ds = None
+        if need_i or need_ls:
+            d_i, ds = _grad(i_f16, t_all_f16, r_stats, c_stats, scale, -rank * n_loc, n_glob,
+                            w_r, w_c, want_dscale=need_ls)
+        if need_t:
+            d_t_all, ds_t = _grad(t_all_f16, i_f16, c_stats, r_stats, scale, rank * n_loc,
+                                  n_glob, w_c, w_r, want_dscale=(need_ls and ds is None))
+            if ds is None:
+                ds = ds_t
+            if world > 1:
+                d_t = torch.empty(n_loc, d_t_all.shape[1], dtype=torch.float32, device=d_t_all.device)
+                _dist().reduce_scatter_tensor(d_t, d_t_all, group=ctx.group)
+            else:
+                d_t = d_t_all
+        if need_ls:
+            if world > 1:
+                _dist().all_reduce(ds, group=ctx.group)
+            # d/dl clamp(e^l, max=100) = e^l if e^l <= 100 else 0   (reference :456-457)
+            d_ls = ds * (0.0 if ctx.clamped else ctx.exp_ls)
+            d_ls = (d_ls * mul * gs).to(ctx.in_dtypes[2]).reshape(ctx.ls_shape)
+        if need_i:
+            d_i = (d_i * (mul * gs)).to(ctx.in_dtypes[0])
+        else:
+            d_i = None
+        if need_t:
+            d_t = (d_t * (mul * gs)).to(ctx.in_dtypes[1])
+        return d_i, d_t, d_ls, None, None, None, None, None, None
+
+
+def fused_clip_loss_from_embeddings(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor,
+                                    logit_scale: torch.Tensor, *, group=None,
+                                    grad_scale: float = 1.0,
+                                    _operands=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Symmetric InfoNCE loss of already L2-normalised embeddings.
+
+    Equivalent to the reference's ``logits = (I @ T.T) * clamp(exp(logit_scale), max=100)``
+    followed by ``_compute_loss(logits)`` (VisionLanguageModule.py:456-459, 533-552), returning
+    ``(loss, image_loss, text_loss)``.  The embeddings are consumed as bf16 (values that are
+    bf16-representable are used exactly); accumulation is fp32.  ``group``: torch.distributed
+    process group for the sharded global-batch variant (each rank passes its local rows);
+    ``grad_scale`` multiplies every gradient (use ``world_size`` under DDP gradient averaging).
+    """
+    i_bf16 = t_bf16 = i_f16 = t_f16 = None
+    if _operands is not None:
+        i_bf16, t_bf16, i_f16, t_f16 = _operands
+    return _FusedClipLoss.apply(image_embeddings, text_embeddings, logit_scale, i_bf16, t_bf16,
+                                i_f16, t_f16, group, grad_scale)
+
+
+# ----------------------------------------------------------------------------------------------
+# prologue: projection + L2 normalise
+# ----------------------------------------------------------------------------------------------
+def _gemm_tf32(a, b, m, n, k, trans_a, trans_b):
+    lib = _lib.load()
+    c = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    nbytes = lib.vlpclip_gemm_workspace_bytes(m, n, k)
+    ws = _ws(nbytes, a.device)
+    rc = lib.vlpclip_gemm_tf32(a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, int(trans_a),
+                               int(trans_b), ws.data_ptr(), nbytes, _stream())
+    _lib.check(rc, "gemm_tf32")
+    return c
+
+
+class _ProjectNormalize(torch.autograd.Function):
+    """emb = F.normalize(features @ W)  (reference :448-449, :452-453)."""
+
+    @staticmethod
+    def forward(ctx, features, weight):
+        _require_cuda(features, "features")
+        _require_cuda(weight, "projection")
+        if features.dim() != 2 or weight.dim() != 2 or features.shape[1] != weight.shape[0]:
+            raise ValueError(f"shape mismatch: features {tuple(features.shape)} @ projection "
+                             f"{tuple(weight.shape)}")
+        f32 = features.detach().float().contiguous()
+        w32 = weight.detach().float().contiguous()
+        n, f = f32.shape
+        d = w32.shape[1]
+        lib = _lib.load()
+        dev = f32.device
+        emb = torch.empty(n, d, dtype=torch.float32, device=dev)
+        emb_bf16 = torch.empty(n, d, dtype=torch.bfloat16, device=dev)
+        emb_f16 = torch.empty(n, d, dtype=torch.float16, device=dev)
+        inv_norm = torch.empty(n, dtype=torch.float32, device=dev)
+        nbytes = lib.vlpclip_project_workspace_bytes(n, f, d)
+        ws = _ws(nbytes, dev)
+        rc = lib.vlpclip_project_normalize_fwd(f32.data_ptr(), w32.data_ptr(), n, f, d,
+                                               emb.data_ptr(), emb_bf16.data_ptr(),
+                                               emb_f16.data_ptr(), inv_norm.data_ptr(),
+                                               ws.data_ptr(), nbytes, _stream())
+        _lib.check(rc, "project_normalize_fwd")
+        ctx.save_for_backward(f32, w32, emb, inv_norm)
+        ctx.in_dtypes = (features.dtype, weight.dtype)
+        ctx.mark_non_differentiable(emb_bf16, emb_f16)
+        return emb, emb_bf16, emb_f16
+
+    @staticmethod
+    def backward(ctx, d_emb, _g1, _g2):
+        f32, w32, emb, inv_norm = ctx.saved_tensors
+        if d_emb is None:
+            return None, None
+        n, f = f32.shape
+        d = w32.shape[1]
+        lib = _lib.load()
+        d_emb = d_emb.float().contiguous()
+        du = torch.empty_like(emb)
+        _lib.check(lib.vlpclip_normalize_bwd(emb.data_ptr(), d_emb.data_ptr(), inv_norm.data_ptr(),
+                                             n, d, du.data_ptr(), _stream()), "normalize_bwd")
+        d_feat = d_w = None
+        if ctx.needs_input_grad[0]:
+            d_feat = _gemm_tf32(du, w32, n, f, d, 0, 1).to(ctx.in_dtypes[0])      # du @ W^T
+        if ctx.needs_input_grad[1]:
+            d_w = _gemm_tf32(f32, du, f, d, n, 1, 0).to(ctx.in_dtypes[1])          # feat^T @ du
+        return d_feat, d_w
+
+
+def project_normalize(features: torch.Tensor, projection: torch.Tensor):
+    """(emb_fp32, emb_bf16, emb_f16) = normalize(features @ projection)."""
+    return _ProjectNormalize.apply(features, projection)
+
+
+def fused_clip_loss(image_features: torch.Tensor, text_features: torch.Tensor,
+                    image_projection: torch.Tensor, text_projection: torch.Tensor,
+                    logit_scale: torch.Tensor, *, group=None, grad_scale: float = 1.0):
+    """Full head: returns (loss, image_loss, text_loss, image_embeddings, text_embeddings).
+
+    Same results as the reference ``forward`` (:448-459) + ``_compute_loss`` (:533-552) on the
+    encoder outputs, with the loss evaluated on the bf16-rounded embeddings.
+    """
+    i_emb, i_bf16, i_f16 = project_normalize(image_features, image_projection)
+    t_emb, t_bf16, t_f16 = project_normalize(text_features, text_projection)
+    loss, il, tl = fused_clip_loss_from_embeddings(
+        i_emb, t_emb, logit_scale, group=group, grad_scale=grad_scale,
+        _operands=(i_bf16, t_bf16, i_f16, t_f16))
+    return loss, il, tl, i_emb, t_emb
+
+
+def clip_lse_stats(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor,
+                   logit_scale_value: float):
+    """Forward-only helper: (row_lse, col_lse, diag_logit) in natural-log units (no autograd)."""
+    s = min(math.exp(float(logit_scale_value)), LOGIT_SCALE_MAX)
+    ib = image_embeddings.detach().to(torch.bfloat16).contiguous()
+    tb = text_embeddings.detach().to(torch.bfloat16).contiguous()
+    rm, rl, rdiag = lse_stats(ib, tb, s, 0)
+    cm, cl, cdiag = lse_stats(tb, ib, s, 0)
+    row_lse = merge_stats(rm, rl, rdiag, s, want_lse=True)[4]
+    col_lse = merge_stats(cm, cl, cdiag, s, want_lse=True)[4]
+    return row_lse, col_lse, rdiag * s
