@@ -6,7 +6,6 @@
  *     :456-459  clamp(exp(logit_scale)) scaled N x N similarity -> fused into vlpclip_lse_fwd / vlpclip_grad
  *     :550-552  row / column cross-entropy                      -> vlpclip_lse_fwd + vlpclip_lse_merge + vlpclip_loss_reduce
  *     autograd of the above (triggered after :645)              -> vlpclip_grad, vlpclip_normalize_bwd
- *     :364-439  retrieval metrics (the "next" row f1)           -> vlpclip_topk_rows
  *
  * The reference has no FFI of its own (pure Python over torch ops); the Python host side binds
  * these symbols with ctypes. Conventions:
@@ -114,16 +113,6 @@ int vlpclip_normalize_bwd(const float* emb_f32, const float* d_emb, const float*
 int vlpclip_gemm_tf32(const float* a, const float* b, float* c, int m, int n, int k, int trans_a,
                       int trans_b, void* workspace, size_t workspace_bytes, void* stream);
 size_t vlpclip_gemm_workspace_bytes(int m, int n, int k);
-
-/* ---- retrieval metrics without the M x M matrix (reference :364-439) ----
- * For every row i of X (bf16 [n_rows, d]): the indices of the k (<= 16) largest <X_i, Y_j>,
- * ties broken towards the smaller index, sorted by descending similarity.
- * out_idx: [n_rows, k] int32.
- */
-size_t vlpclip_topk_workspace_bytes(int n_rows, int n_cols, int d, int k);
-int vlpclip_topk_rows(const void* x_bf16, int ldx, const void* y_bf16, int ldy, int n_rows,
-                      int n_cols, int d, int k, int32_t* out_idx, void* workspace,
-                      size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

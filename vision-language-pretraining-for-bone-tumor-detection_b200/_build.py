@@ -14,7 +14,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libvlpclip.so")
-SOURCES = ["lse_fwd.cu", "grad_bwd.cu", "prologue.cu", "topk.cu"]
+SOURCES = ["lse_fwd.cu", "grad_bwd.cu", "prologue.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

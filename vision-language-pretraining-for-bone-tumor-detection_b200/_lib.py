@@ -38,9 +38,6 @@ _SIGNATURES = {
     "vlpclip_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlpclip_gemm_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_size_t, c_void_p]),
-    "vlpclip_topk_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "vlpclip_topk_rows": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                  c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 

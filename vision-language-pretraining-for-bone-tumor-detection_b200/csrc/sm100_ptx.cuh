@@ -241,7 +241,7 @@ VLP_DEVICE void tc_fence_after() {
 // ----------------------------------------------------------------------------
 // tcgen05: descriptors
 // ----------------------------------------------------------------------------
-enum : uint32_t { UMMA_F16 = 0, UMMA_BF16 = 1 };
+enum : uint32_t { UMMA_F16 = 0, UMMA_BF16 = 1, UMMA_TF32 = 2 };
 enum : uint32_t { MAJOR_K = 0, MAJOR_MN = 1 };
 
 // kind::f16 instruction descriptor, fp32 accumulate
@@ -298,6 +298,20 @@ VLP_DEVICE void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint3
         : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+
+// kind::tf32: fp32 operands in smem (K = 8 per instruction), fp32 accumulate
+VLP_DEVICE void umma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // A operand from tensor memory (K-major only), B from shared memory
