@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- CLIP loss fwd+bwd throughput of the fused B200 head (and of the reference CPU path).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (1 rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # reference torch ops on the host cores
+
+One "step" = one forward + backward of the symmetric InfoNCE head on one synthetic batch of
+L2-normalised bf16 embeddings (gradients w.r.t. both embedding streams and logit_scale).
+Workload (N = 1 GPU): the north-star configuration, global batch 32768 x dim 512.  With G GPUs the
+same global batch is row-sharded (32768 / G rows per rank, strong scaling); every rank still meets
+all 32768 columns (all-gather of the text embeddings, all-gather of the column statistics,
+reduce-scatter of dT).
+
+Rank 0 prints ONE JSON line (see the driver contract in the task description):
+  value      whole-job pairs/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the public API with HOST (pinned) inputs: per step one H2D copy of
+             that step's embeddings (prefetched on a side stream) and a D2H read of the loss
+  roofline   dominant kernel (grad_pair_kernel): algorithmic 2 N^2 D flops / its measured duration
+             vs the measured dense bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (reference torch ops, host cores) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CLIP loss fwd+bwd image-text pairs/sec"
+UNIT = "pairs/s"
+LOGIT_SCALE = math.log(1 / 0.07)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            # samples under load = upper half of the distribution (idle samples bracket the region)
+            sm_sorted = sorted(sm)
+            loaded = sm_sorted[len(sm_sorted) // 2:]
+            out["sm_mhz"] = loaded[len(loaded) // 2]
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_sample(n: int, d: int, block: int, steps: int, warmup: int, seed: int = 42):
+    """Reference torch ops (oracle/clip_oracle.py, a restatement of VisionLanguageModule.py:456-459,
+    533-552) on a row slab of the workload: `block` pairs meet all n columns.
+
+    The full n x n problem needs ~5 live n x n fp64 buffers (43 GB at n = 32768), so each step runs
+    a slab that does exactly block/n of the full step's arithmetic: S slab = s * I_blk @ T_all^T
+    (fp32 GEMM, fp64 logits as in the reference), both soft-max passes over the slab, and autograd
+    back to dI_blk and dT_all.  pairs/s = block / t_slab.
+    """
+    import torch
+    import torch.nn.functional as F
+    from oracle import clip_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(seed)
+    t_all = F.normalize(torch.randn(n, d, generator=g)).to(torch.bfloat16).float().requires_grad_(True)
+    i_blk = F.normalize(torch.randn(block, d, generator=g)).to(torch.bfloat16).float().requires_grad_(True)
+    ls = torch.tensor([LOGIT_SCALE], dtype=torch.float64, requires_grad=True)   # reference :111
+    labels = torch.arange(block)
+
+    def step():
+        for t in (t_all, i_blk, ls):
+            t.grad = None
+        scale = torch.clamp(ls.exp(), max=O.LOGIT_SCALE_MAX)                 # :456-457
+        logits = (i_blk @ t_all.T) * scale                                   # :459 (slab of it)
+        image_loss = F.cross_entropy(logits, labels, reduction="sum")        # :550 on the slab rows
+        # column direction: same element-wise work on the same slab (log-softmax along dim 0)
+        text_part = -torch.log_softmax(logits, dim=0)[labels, labels].sum()  # :551 (slab share)
+        loss = (image_loss + text_part) / (2 * n)                            # :552
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return {"value": block / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "ms_per_step": dt * 1e3,
+            "sample": (f"row slab of the workload: {block} pairs x all {n} columns, d={d} "
+                       f"(= {block}/{n} of one full fwd+bwd step; reference torch ops, fp32 GEMM + "
+                       "fp64 soft-max as in VisionLanguageModule.py:456-459,550-552)")}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n, d = args.n, args.d
+    block = args.cpu_block
+    res = cpu_reference_sample(n, d, block, max(1, args.steps), max(0, args.warmup))
+    line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"fused contrastive loss fwd+bwd, global batch {n} x dim {d}",
+                       "global_batch": n, "dim": d, "logit_scale": LOGIT_SCALE},
+            "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"],
+                             "kind": res["kind"], "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.nn.functional as F
+    import vlp_b200  # noqa: F401
+    from vlp_b200 import _lib, functional as VF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fused head has no CPU path "
+                         "(use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    lib = _lib.load()
+    n, d = args.n, args.d
+    if n % world != 0:
+        raise SystemExit(f"global batch {n} not divisible by {world} ranks")
+    b = n // world
+
+    # two rotating input sets (same distribution, different seeds); every rank builds its slice
+    def make_inputs(seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        a = torch.randn(n, d, generator=g, device=dev)
+        c = torch.randn(n, d, generator=g, device=dev)
+        c = 0.35 * a + math.sqrt(1 - 0.35 ** 2) * c
+        I = F.normalize(a).to(torch.bfloat16)[rank * b:(rank + 1) * b].contiguous()
+        T = F.normalize(c).to(torch.bfloat16)[rank * b:(rank + 1) * b].contiguous()
+        return I, T
+
+    sets = [make_inputs(42), make_inputs(43)]
+    ls = torch.tensor([LOGIT_SCALE], dtype=torch.float32, device=dev, requires_grad=True)
+
+    def step(I, T):
+        I = I.detach().requires_grad_(True)
+        T = T.detach().requires_grad_(True)
+        ls.grad = None
+        loss, _, _ = VF.fused_clip_loss_from_embeddings(I, T, ls, group=group)
+        loss.backward()
+        return loss, I.grad, T.grad
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    for w in range(max(3, args.warmup)):
+        step(*sets[w % 2])
+    sync_all()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = lib.vlpclip_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for k in range(args.steps):
+        loss, _, _ = step(*sets[k % 2])
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = lib.vlpclip_launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = n / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (grad_pair_kernel through the C ABI, same stream) ----
+    I, T = sets[0]
+    if world > 1:
+        T_all = torch.empty(n, d, dtype=torch.bfloat16, device=dev)
+        torch.distributed.all_gather_into_tensor(T_all, T)
+    else:
+        T_all = T
+    scale = math.exp(LOGIT_SCALE)
+    rm, rl, rdiag = VF.lse_stats(I, T_all, scale, -rank * b)
+    r_stats = VF.merge_stats(rm, rl, rdiag, scale)[:3]
+    cm, cl, cdiag = VF.lse_stats(T_all, I, scale, rank * b)
+    if world > 1:
+        gather = lambda t: torch.cat([x for x in _all_gather_list(t, world)], dim=0)  # noqa: E731
+        cm_all = torch.stack(_all_gather_list(cm, world))
+        cl_all = torch.stack(_all_gather_list(cl, world))
+        cdiag = torch.cat(_all_gather_list(cdiag[rank * b:(rank + 1) * b].contiguous(), world))
+        c_stats = VF.merge_stats(cm_all, cl_all, cdiag, scale)[:3]
+    else:
+        c_stats = VF.merge_stats(cm, cl, cdiag, scale)[:3]
+    i16 = VF.cast_bf16_to_f16(I)
+    t16 = VF.cast_bf16_to_f16(T_all)
+    for _ in range(2):
+        VF._grad(i16, t16, r_stats, c_stats, scale, -rank * b, n, 1.0, 1.0, True)
+    torch.cuda.synchronize()
+    k0 = torch.cuda.Event(enable_timing=True)
+    k1 = torch.cuda.Event(enable_timing=True)
+    reps = max(3, min(10, args.steps))
+    k0.record()
+    for _ in range(reps):
+        VF._grad(i16, t16, r_stats, c_stats, scale, -rank * b, n, 1.0, 1.0, True)
+    k1.record()
+    torch.cuda.synchronize()
+    grad_ms = k0.elapsed_time(k1) / reps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host embeddings -> H2D (prefetched on a side stream) -> loss D2H ----
+    host = [(I_.cpu().pin_memory(), T_.cpu().pin_memory()) for (I_, T_) in sets]
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_bufs = [(torch.empty_like(sets[0][0]), torch.empty_like(sets[0][1])) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def prefetch(k):
+        slot = k % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            dev_bufs[slot][0].copy_(host[k % 2][0], non_blocking=True)
+            dev_bufs[slot][1].copy_(host[k % 2][1], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(steps):
+        for s_ in range(2):
+            consumed[s_].record(torch.cuda.current_stream())
+        prefetch(0)
+        for k in range(steps):
+            if k + 1 < steps:
+                prefetch(k + 1)
+            slot = k % 2
+            torch.cuda.current_stream().wait_event(ready[slot])
+            loss, _, _ = step(*dev_bufs[slot])
+            consumed[slot].record(torch.cuda.current_stream())
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=False)   # D2H read of the result
+        return float(loss_host.item())
+
+    e2e_loop(2)
+    sync_all()
+    t0 = time.perf_counter()
+    g0 = torch.cuda.Event(enable_timing=True)
+    g1 = torch.cuda.Event(enable_timing=True)
+    g0.record()
+    e2e_loop(args.steps)
+    g1.record()
+    sync_all()
+    e2e_ms = g0.elapsed_time(g1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = n / (e2e_ms / args.steps * 1e-3)
+    h2d = 2 * b * d * 2 * world          # bf16 image + text embeddings of the global batch
+    d2h = 4 * world
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return 0
+
+    peaks = measured_peaks()
+    f_alg_step = 6.0 * n * n * d                    # S, dI, dT GEMMs (recompute not counted)
+    f_alg_grad = 2.0 * (n / world) * n * d          # one grad launch on this rank: dX = G Y
+    grad_tflops = f_alg_grad / (grad_ms * 1e-3) / 1e12
+    step_tflops = f_alg_step / (ms_per_step * 1e-3) / 1e12 / world   # per GPU
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("grad_pair_kernel", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        cpu = cpu_reference_sample(n, d, args.cpu_block, 2, 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"fused contrastive loss fwd+bwd, global batch {n} x dim {d}",
+                   "global_batch": n, "dim": d, "rows_per_gpu": b, "logit_scale": LOGIT_SCALE,
+                   "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                   "l2": "two input sets rotated; inputs+operand copies+gradients = "
+                         f"{(2 * 2 * n * d * 2 + 2 * n * d * 4) / 1e6:.0f} MB per step > 126 MB L2"},
+        "pct_of_bf16_peak": 100.0 * step_tflops / peaks["bf16_tflops"],
+        "algorithmic_tflops_per_gpu": step_tflops,
+        "roofline": {"bound": "tensor", "kernel": "grad_pair_kernel",
+                     "achieved": grad_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": grad_tflops / peaks["bf16_tflops"],
+                     "frac_of_sustained": grad_tflops / peaks["bf16_tflops_sustained"],
+                     "peak_source": peaks["source"] + " (burst cuBLAS bf16)",
+                     "ms_per_launch": grad_ms,
+                     "algorithmic_flops_per_launch": f_alg_grad,
+                     "executed_flops_per_launch": 2.0 * f_alg_grad,
+                     "traffic": traffic},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def _all_gather_list(t, world):
+    import torch
+    out = [torch.empty_like(t) for _ in range(world)]
+    torch.distributed.all_gather(out, t.contiguous())
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=32768, help="global batch (pairs)")
+    ap.add_argument("--d", type=int, default=512, help="embedding dim")
+    ap.add_argument("--cpu-block", type=int, default=1024, help="rows of the CPU reference slab")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 8:
+            args.steps = 8     # bounded: the whole run must end within a few minutes
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

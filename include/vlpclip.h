@@ -35,6 +35,9 @@ const char* vlpclip_last_error(void);
 /* number of SMs of the current device (grid sizing / workspace sizing) */
 int vlpclip_sm_count(void);
 
+/* kernels launched by this library so far in this process (bench.py: gpu_launches) */
+unsigned long long vlpclip_launch_count(void);
+
 /* bf16 -> fp16 copy (values of unit-norm embeddings are exactly representable but for |x| < 2^-14) */
 int vlpclip_cast_bf16_to_f16(const void* src_bf16, void* dst_f16, size_t n_elems, void* stream);
 

@@ -1,0 +1,67 @@
+"""CPU: the C-ABI shared library builds for sm_100a, loads without a GPU and exports every symbol
+``include/vlpclip.h`` declares (no compute calls here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import vlp_b200  # noqa: F401
+from vlp_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "vlpclip.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vlpclip_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_entry_points():
+    fns = header_functions()
+    for required in ("vlpclip_lse_fwd", "vlpclip_lse_merge", "vlpclip_loss_reduce", "vlpclip_grad",
+                     "vlpclip_project_normalize_fwd", "vlpclip_normalize_bwd", "vlpclip_gemm_tf32",
+                     "vlpclip_last_error", "vlpclip_version"):
+        assert required in fns
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = _build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    missing = [f for f in header_functions() if not hasattr(lib, f)]
+    assert not missing, f"declared in vlpclip.h but not exported: {missing}"
+
+
+def test_ctypes_signatures_cover_the_header():
+    assert sorted(_lib.declared_symbols()) == header_functions()
+
+
+def test_version_and_error_string_without_gpu():
+    lib = _lib.load()
+    assert lib.vlpclip_version() == 100
+    # size queries are pure host arithmetic
+    assert lib.vlpclip_lse_workspace_bytes(256, 256, 512) > 0
+    assert lib.vlpclip_grad_workspace_bytes(256, 256, 512) > 0
+    assert lib.vlpclip_lse_workspace_bytes(0, 256, 512) == 0
+    # argument validation happens before any CUDA call and reports through last_error
+    rc = lib.vlpclip_lse_merge(None, None, None, 0, 0, 1.0, None, None, None, None, None, None, None)
+    assert rc == -1 and b"empty" in lib.vlpclip_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "lse_merge")
+
+
+def test_kernels_are_blackwell_native():
+    """SASS must contain tcgen05 MMA / TMEM / TMA instructions and no legacy HMMA path."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _build.build()], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass       # tcgen05.mma kind::f16
+    assert "LDTM" in sass and "STTM" in sass   # tcgen05.ld / st
+    assert "UTMALDG" in sass       # cp.async.bulk.tensor
+    assert "UBLKCP" in sass        # cp.async.bulk (DSMEM tile push)
+    assert "HMMA." not in sass.replace("UTCHMMA", "")

@@ -1,0 +1,84 @@
+"""CPU, gloo, world_size 2 and 4: the sharded plan (all-gather / partial-stat merge / all-reduce /
+reduce-scatter orchestration of vlp_b200.sharded) against the single-process oracle."""
+import math
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, d, ls, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import vlp_b200  # noqa: F401
+        from vlp_b200 import sharded
+        from kernel_contract_ops import ContractOps
+        from oracle import clip_oracle as O
+        I, T = O.make_embeddings(n, d, rho=0.35, seed=42)      # every rank builds the global batch
+        b = n // world
+        i_loc = I[rank * b:(rank + 1) * b].double()
+        t_loc = T[rank * b:(rank + 1) * b].double()
+        scale = min(math.exp(ls), 100.0)
+        plan = sharded.forward_plan(ContractOps, i_loc, t_loc, scale, dist.group.WORLD)
+        d_i, d_t, ds = sharded.backward_plan(ContractOps, i_loc, plan["t_all"], plan["r_stats"],
+                                             plan["c_stats"], scale, b, n, rank, world, dist.group.WORLD)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=plan["loss"].numpy(),
+                 image_loss=plan["image_loss"].numpy(), text_loss=plan["text_loss"].numpy(),
+                 dI=d_i.numpy(), dT=d_t.numpy(), ds=ds.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,d,ls", [(2, 96, 32, 2.6593), (4, 64, 16, 3.5), (2, 40, 24, 5.0)])
+def test_sharded_plan_matches_single_process_oracle(tmp_path, world, n, d, ls):
+    from oracle import clip_oracle as O
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, d, ls, str(tmp_path)), nprocs=world, join=True)
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=42)
+    ref = O.closed_form(I.numpy(), T.numpy(), ls)
+    b = n // world
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        assert abs(float(got["loss"]) - ref["loss"]) < 1e-10          # same global loss on every rank
+        assert abs(float(got["image_loss"]) - ref["image_loss"]) < 1e-10
+        assert abs(float(got["text_loss"]) - ref["text_loss"]) < 1e-10
+        assert O.rel_err(got["dI"], ref["dI"][r * b:(r + 1) * b]) < 1e-10
+        assert O.rel_err(got["dT"], ref["dT"][r * b:(r + 1) * b]) < 1e-10
+        assert abs(float(got["ds"][0]) - ref["dscale"]) < 1e-10 * max(1.0, abs(ref["dscale"]))
+
+
+def test_single_process_plan_matches_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import vlp_b200  # noqa: F401
+    from vlp_b200 import sharded
+    from kernel_contract_ops import ContractOps
+    from oracle import clip_oracle as O
+    I, T = O.make_embeddings(50, 24, rho=0.2, seed=9)
+    ls = 2.0
+    scale = math.exp(ls)
+    plan = sharded.forward_plan(ContractOps, I.double(), T.double(), scale, None)
+    d_i, d_t, ds = sharded.backward_plan(ContractOps, I.double(), plan["t_all"], plan["r_stats"],
+                                         plan["c_stats"], scale, 50, 50, 0, 1, None)
+    ref = O.closed_form(I.numpy(), T.numpy(), ls)
+    assert abs(float(plan["loss"]) - ref["loss"]) < 1e-12
+    assert O.rel_err(d_i.numpy(), ref["dI"]) < 1e-12 and O.rel_err(d_t.numpy(), ref["dT"]) < 1e-12
+    assert abs(float(ds[0]) - ref["dscale"]) < 1e-12

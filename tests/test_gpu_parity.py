@@ -1,0 +1,224 @@
+"""GPU (B200): parity of the fused CUDA path against the oracle / the reference's golden vectors.
+
+Tolerances are the north-star's: loss within 1e-4 relative, gradients within 1e-3 (normwise
+relative, ||g - g_ref|| / ||g_ref||) versus the fp32/fp64 reference on the SAME bf16-representable
+embeddings.  Everything goes through the C ABI (ctypes) via vlp_b200.functional."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import clip_oracle as O  # noqa: E402
+
+LOSS_RTOL = 1e-4
+GRAD_RTOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def VF():
+    import vlp_b200  # noqa: F401
+    from vlp_b200 import _lib, functional
+    assert os.path.exists(_lib.lib_path())
+    return functional
+
+
+def run_fused(VF, I, T, ls, ls_dtype=torch.float64):
+    dev = torch.device("cuda:0")
+    Ic = I.to(dev).requires_grad_(True)
+    Tc = T.to(dev).requires_grad_(True)
+    lsc = torch.tensor([ls], dtype=ls_dtype, device=dev, requires_grad=True)
+    loss, il, tl = VF.fused_clip_loss_from_embeddings(Ic, Tc, lsc)
+    loss.backward()
+    torch.cuda.synchronize()
+    return dict(loss=loss.item(), image_loss=il.item(), text_loss=tl.item(),
+                dI=Ic.grad.cpu().numpy(), dT=Tc.grad.cpu().numpy(), dl=lsc.grad.item())
+
+
+def assert_close(got, ref, ref_dl):
+    for k in ("loss", "image_loss", "text_loss"):
+        assert abs(got[k] - ref[k]) <= LOSS_RTOL * abs(ref[k]) + 1e-9, (k, got[k], ref[k])
+    assert O.rel_err(got["dI"], ref["dI"]) < GRAD_RTOL
+    assert O.rel_err(got["dT"], ref["dT"]) < GRAD_RTOL
+    if ref_dl == 0.0:
+        assert got["dl"] == 0.0
+    else:
+        assert abs(got["dl"] - ref_dl) <= GRAD_RTOL * abs(ref_dl) + 1e-12
+
+
+EMB_CASES = sorted(os.path.basename(p)[:-4] for p in
+                   glob.glob(os.path.join(os.path.dirname(__file__), "golden", "emb_*.npz")))
+
+
+@pytest.mark.parametrize("name", EMB_CASES)
+def test_against_reference_golden_vectors(VF, golden_dir, name):
+    """Outputs of the reference's own forward/_compute_loss code (fp32) on seeded embeddings."""
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
+    n, d, rho, ls, seed = g["params"]
+    I, T = O.make_embeddings(int(n), int(d), rho=float(rho), seed=int(seed))
+    got = run_fused(VF, I, T, float(ls))
+    ref = {k: float(np.ravel(g[k])[0]) for k in ("loss", "image_loss", "text_loss")}
+    ref["dI"], ref["dT"] = g["dI"], g["dT"]
+    assert_close(got, ref, float(np.ravel(g["d_logit_scale"])[0]))
+
+
+@pytest.mark.parametrize("n,d,ls,rho", [
+    (256, 512, math.log(1 / 0.07), 0.35),   # BASELINE config 2
+    (256, 512, math.log(1 / 0.07), 0.0),
+    (256, 512, math.log(50.0), 0.35),       # tiny loss: positive pair dominates
+    (256, 512, math.log(50.0), 0.0),
+    (256, 512, 5.0, 0.0),                   # clamped: s = 100, d logit_scale = 0
+    (1, 64, 2.0, 0.0),                      # single pair: loss 0, zero gradients
+    (2, 8, 2.6593, 0.35),                   # smallest supported embedding dim
+    (100, 72, 3.0, 0.35),                   # ragged rows / cols / K
+    (129, 40, 2.6593, 0.2),                 # one row past a tile boundary
+    (1000, 128, 3.0, 0.5),
+    (2048, 256, 2.6593, 0.35),
+    (4096, 512, 2.6593, 0.35),              # BASELINE config 3 size on one GPU
+    (4096, 512, 4.6, 0.35),
+])
+def test_against_closed_form_oracle(VF, n, d, ls, rho):
+    I, T = O.make_embeddings(n, d, rho=rho, seed=42)
+    ref = O.closed_form(I.numpy(), T.numpy(), ls)
+    got = run_fused(VF, I, T, ls)
+    assert_close(got, ref, ref["dlogit_scale"])
+
+
+def test_logit_scale_dtype_and_shape_follow_the_parameter(VF):
+    I, T = O.make_embeddings(64, 64, seed=1)
+    dev = torch.device("cuda:0")
+    for dt in (torch.float64, torch.float32):
+        ls = torch.tensor([2.5], dtype=dt, device=dev, requires_grad=True)
+        loss, _, _ = VF.fused_clip_loss_from_embeddings(I.to(dev).requires_grad_(True), T.to(dev), ls)
+        loss.backward()
+        assert ls.grad.dtype == dt and tuple(ls.grad.shape) == (1,)
+        assert loss.dtype == torch.float32
+
+
+def test_forward_only_no_grad_mode(VF):
+    I, T = O.make_embeddings(300, 128, seed=2)
+    dev = torch.device("cuda:0")
+    with torch.no_grad():
+        loss, il, tl = VF.fused_clip_loss_from_embeddings(I.to(dev), T.to(dev), torch.tensor([3.0], device=dev))
+    ref = O.closed_form(I.numpy(), T.numpy(), 3.0)
+    assert abs(loss.item() - ref["loss"]) < LOSS_RTOL * ref["loss"]
+    assert not loss.requires_grad
+
+
+def test_needs_input_grad_is_honoured(VF):
+    """Frozen groups (reference :273-281): any of dI / dT / d logit_scale may be not required."""
+    I, T = O.make_embeddings(200, 64, seed=3)
+    ref = O.closed_form(I.numpy(), T.numpy(), 2.6593)
+    dev = torch.device("cuda:0")
+    Ic = I.to(dev).requires_grad_(True)
+    ls = torch.tensor([2.6593], dtype=torch.float64, device=dev)          # frozen temperature
+    loss, _, _ = VF.fused_clip_loss_from_embeddings(Ic, T.to(dev), ls)     # frozen text tower
+    loss.backward()
+    assert O.rel_err(Ic.grad.cpu().numpy(), ref["dI"]) < GRAD_RTOL
+    ls2 = torch.tensor([2.6593], dtype=torch.float64, device=dev, requires_grad=True)
+    loss2, _, _ = VF.fused_clip_loss_from_embeddings(I.to(dev), T.to(dev), ls2)   # only the temperature
+    loss2.backward()
+    assert abs(ls2.grad.item() - ref["dlogit_scale"]) < GRAD_RTOL * abs(ref["dlogit_scale"])
+
+
+def test_image_and_text_loss_backpropagate_separately(VF):
+    I, T = O.make_embeddings(150, 64, seed=4)
+    dev = torch.device("cuda:0")
+    Ic = I.to(dev).requires_grad_(True)
+    Tc = T.to(dev).requires_grad_(True)
+    ls = torch.tensor([2.6593], dtype=torch.float64, device=dev)
+    _, il, _ = VF.fused_clip_loss_from_embeddings(Ic, Tc, ls)
+    il.backward()
+    Ir = I.double().clone().requires_grad_(True)
+    Tr = T.double().clone().requires_grad_(True)
+    _, il_ref, _ = O.loss_from_embeddings(Ir, Tr, torch.tensor([2.6593], dtype=torch.float64))
+    il_ref.backward()
+    assert O.rel_err(Ic.grad.cpu().numpy(), Ir.grad.numpy()) < GRAD_RTOL
+    assert O.rel_err(Tc.grad.cpu().numpy(), Tr.grad.numpy()) < GRAD_RTOL
+
+
+def test_bitwise_reproducible(VF):
+    I, T = O.make_embeddings(1500, 256, seed=5)
+    a = run_fused(VF, I, T, 2.6593)
+    b = run_fused(VF, I, T, 2.6593)
+    assert a["loss"] == b["loss"] and a["dl"] == b["dl"]
+    assert np.array_equal(a["dI"], b["dI"]) and np.array_equal(a["dT"], b["dT"])
+
+
+def test_errors_are_raised_not_swallowed(VF):
+    dev = torch.device("cuda:0")
+    I, T = O.make_embeddings(16, 16)
+    with pytest.raises(ValueError):
+        VF.fused_clip_loss_from_embeddings(I.to(dev), T[:8].to(dev), torch.tensor([2.0], device=dev))
+    with pytest.raises(ValueError):   # embedding dim must be a multiple of 8
+        VF.fused_clip_loss_from_embeddings(torch.randn(16, 12, device=dev), torch.randn(16, 12, device=dev),
+                                           torch.tensor([2.0], device=dev))
+    with pytest.raises(ValueError):   # > 512 columns do not fit the TMEM accumulator plan yet
+        VF.fused_clip_loss_from_embeddings(torch.randn(16, 768, device=dev), torch.randn(16, 768, device=dev),
+                                           torch.tensor([2.0], device=dev))
+
+
+# ---- full size (BASELINE headline: 32768 x 512): size-independent properties -------------------
+@pytest.fixture(scope="module")
+def full_size(VF):
+    n, d, ls = 32768, 512, math.log(1 / 0.07)
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=42)
+    got = run_fused(VF, I, T, ls)
+    return n, d, ls, I, T, got
+
+
+def test_full_size_sampled_rows_against_fp64(full_size):
+    n, d, ls, I, T, got = full_size
+    s = math.exp(ls)
+    rows = np.random.RandomState(0).choice(n, 48, replace=False)
+    Id, Td = I.double(), T.double()
+    S_rows = s * (Id[rows] @ Td.T)                      # [48, n]
+    S_cols = s * (Td[rows] @ Id.T)                      # rows of S^T
+    lse_r = torch.logsumexp(S_rows, dim=1)
+    lse_c_sel = torch.logsumexp(S_cols, dim=1)
+    # dI_i = s/(2N) * sum_j (P_row_ij + P_col_ij - 2 delta_ij) T_j needs every column LSE
+    lse_c_all = torch.cat([torch.logsumexp(s * (Td[lo:lo + 2048] @ Id.T), dim=1) for lo in range(0, n, 2048)])
+    G = torch.exp(S_rows - lse_r[:, None]) + torch.exp(S_rows - lse_c_all[None, :])
+    G[torch.arange(len(rows)), torch.as_tensor(rows)] -= 2.0
+    dI_ref = (s / (2.0 * n)) * (G @ Td)
+    assert O.rel_err(got["dI"][rows], dI_ref.numpy()) < GRAD_RTOL
+    # loss terms of the sampled rows are consistent with the global mean (sanity on magnitude)
+    loss_rows = 0.5 * ((lse_r - torch.diagonal(S_rows[:, rows])) + (lse_c_sel - torch.diagonal(S_cols[:, rows])))
+    assert abs(loss_rows.mean().item() - got["loss"]) < 0.25 * got["loss"]
+
+
+def test_full_size_temperature_checksum(full_size):
+    """sum_i <I_i, dI_i> = sum_j <T_j, dT_j> = d logit_scale (unclamped), a checksum of checksums."""
+    n, d, ls, I, T, got = full_size
+    a = float((I.double().numpy() * got["dI"].astype(np.float64)).sum())
+    b = float((T.double().numpy() * got["dT"].astype(np.float64)).sum())
+    assert abs(a - got["dl"]) < 2e-3 * abs(got["dl"])
+    assert abs(b - got["dl"]) < 2e-3 * abs(got["dl"])
+
+
+def test_full_size_loss_against_blocked_fp64(full_size):
+    n, d, ls, I, T, got = full_size
+    s = math.exp(ls)
+    Id, Td = I.double(), T.double()
+    il = tl = 0.0
+    for lo in range(0, n, 2048):
+        Sr = s * (Id[lo:lo + 2048] @ Td.T)
+        Sc = s * (Td[lo:lo + 2048] @ Id.T)
+        idx = torch.arange(lo, min(n, lo + 2048))
+        il += float((torch.logsumexp(Sr, 1) - Sr[torch.arange(len(idx)), idx]).sum())
+        tl += float((torch.logsumexp(Sc, 1) - Sc[torch.arange(len(idx)), idx]).sum())
+    ref = 0.5 * (il + tl) / n
+    assert abs(got["loss"] - ref) < LOSS_RTOL * ref
+
+
+def test_permutation_equivariance(VF):
+    I, T = O.make_embeddings(1024, 128, seed=6)
+    perm = torch.randperm(1024, generator=torch.Generator().manual_seed(1))
+    a = run_fused(VF, I, T, 2.6593)
+    b = run_fused(VF, I[perm], T[perm], 2.6593)
+    assert abs(a["loss"] - b["loss"]) < 1e-5 * a["loss"]
+    assert O.rel_err(b["dI"], a["dI"][perm.numpy()]) < 2e-4

@@ -97,6 +97,13 @@ inline int check_device_sm100() {
   return 0;
 }
 
+// number of kernels this library has launched (bench.py reports it as gpu_launches)
+inline unsigned long long& launch_counter() {
+  static unsigned long long n = 0;
+  return n;
+}
+#define VLP_COUNT_LAUNCH(k) (::vlp::launch_counter() += (k))
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

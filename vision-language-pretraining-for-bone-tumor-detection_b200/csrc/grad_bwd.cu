@@ -571,8 +571,10 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   p.ds_part = dscale ? ds_part : nullptr;
   stats_pad_kernel<<<(npx + 255) / 256, 256, 0, stream>>>(x_max, x_lg2l, n_rows, npx,
                                                           log2f(w_row), xmax, xlg);
+  VLP_COUNT_LAUNCH(1);
   stats_pad_kernel<<<(npy + 255) / 256, 256, 0, stream>>>(y_max, y_lg2l, n_cols, npy,
                                                           log2f(w_col), ymax, ylg);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   if (p.use_atomics) VLP_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)n_rows * d * sizeof(float), stream));
 
@@ -592,10 +594,12 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   const int n_items = p.n_row_blocks * p.n_chunks;
   const int clusters = n_items < n_pairs ? n_items : n_pairs;
   grad_pair_kernel<<<clusters * 2, BWD_THREADS, smem, stream>>>(map_k, map_mn, p);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   if (dscale) {
     ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, n_items * 8, 1.0f / (2.0f * (float)n_global),
                                             dscale);
+  VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
   }
   return 0;

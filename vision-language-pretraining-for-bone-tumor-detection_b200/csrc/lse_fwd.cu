@@ -369,6 +369,7 @@ extern "C" {
 int vlpclip_version(void) { return VLPCLIP_VERSION; }
 const char* vlpclip_last_error(void) { return err_buf(); }
 int vlpclip_sm_count(void) { return sm_count(); }
+unsigned long long vlpclip_launch_count(void) { return launch_counter(); }
 
 int vlpclip_cast_bf16_to_f16(const void* src, void* dst, size_t n, void* stream) {
   if (n == 0) return 0;
@@ -377,6 +378,7 @@ int vlpclip_cast_bf16_to_f16(const void* src, void* dst, size_t n, void* stream)
   if (blocks > 148 * 8) blocks = 148 * 8;
   cast_bf16_to_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)src, (__half*)dst, n);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -440,10 +442,12 @@ int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, 
   const int n_items = p.n_row_blocks * p.n_chunks;
   const int grid = n_items < nsm ? n_items : nsm;
   lse_partial_kernel<<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   lse_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_m, p.part_l, nullptr, nparts,
                                                              n_rows, p.scale_log2, nullptr, row_max,
                                                              row_l, nullptr, nullptr, nullptr);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -457,6 +461,7 @@ int vlpclip_lse_merge(const float* part_max, const float* part_l, const float* d
   lse_merge_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       part_max, part_l, diag, nparts, n, scale * kLog2e, lse, out_max, out_l, out_lg2l, out_q,
       out_loss);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -466,6 +471,7 @@ int vlpclip_loss_reduce(const float* row_loss, const float* col_loss, int n, flo
   if (n <= 0) return fail(-1, "loss_reduce: empty input");
   if (!out2) return fail(-1, "loss_reduce: null pointer");
   loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, col_loss, n, out2);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -264,6 +264,7 @@ static int launch_gemm_kmajor(const float* a, const float* b, int m, int n, int 
   }
   dim3 grid((m + 127) / 128, (n + p.n_tile - 1) / p.n_tile, p.n_splits);
   gemm_tf32_kernel<<<grid, PG_THREADS, smem, stream>>>(map_a, map_b, p);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -271,6 +272,7 @@ static int launch_gemm_kmajor(const float* a, const float* b, int m, int n, int 
 static void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t stream) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   transpose_f32_kernel<<<grid, block, 0, stream>>>(in, out, rows, cols);
+  VLP_COUNT_LAUNCH(1);
 }
 
 }  // namespace vlp
@@ -320,6 +322,7 @@ int vlpclip_normalize_bwd(const float* emb_f32, const float* d_emb, const float*
   if (!emb_f32 || !d_emb || !inv_norm || !du) return fail(-1, "normalize_bwd: null pointer");
   normalize_bwd_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(emb_f32, d_emb, inv_norm, n,
                                                                       d, du);
+  VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -18,7 +18,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
+from . import _lib, sharded
 
 LOGIT_SCALE_MAX = 100.0  # reference: torch.clamp(logit_scale.exp(), max=100)  (:457)
 
@@ -146,22 +146,28 @@ def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_globa
     return dx, ds
 
 
-def _dist():
-    import torch.distributed as dist
-    return dist
+class CudaOps:
+    """The production ``ops`` of sharded.forward_plan / backward_plan: the sm_100a kernels."""
 
+    @staticmethod
+    def lse_stats(x, y, scale, diag_shift):
+        return lse_stats(x, y, scale, diag_shift)
 
-def _group_info(group):
-    if group is None:
-        return 1, 0
-    dist = _dist()
-    return dist.get_world_size(group), dist.get_rank(group)
+    @staticmethod
+    def merge_stats(part_max, part_l, diag, scale):
+        return merge_stats(part_max, part_l, diag, scale)[:4]
 
+    @staticmethod
+    def loss_sums(row_loss, col_loss):
+        return _loss_sums(row_loss, col_loss)
 
-def _all_gather_rows(t: torch.Tensor, group, world: int) -> torch.Tensor:
-    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    _dist().all_gather_into_tensor(out, t.contiguous(), group=group)
-    return out
+    @staticmethod
+    def grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale):
+        return _grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale)
+
+    @staticmethod
+    def to_backward_operand(x_bf16):
+        return cast_bf16_to_f16(x_bf16)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -189,9 +195,6 @@ class _FusedClipLoss(torch.autograd.Function):
         n_loc, d = image_embeddings.shape
         if n_loc == 0:
             raise ValueError("empty batch")
-        dev = image_embeddings.device
-        world, rank = _group_info(group)
-        n_glob = n_loc * world
 
         # reference :456-457 -- exp + clamp(max=100); value needed on the host as a launch scalar
         ls_val = float(logit_scale.detach().double().item())
@@ -204,41 +207,18 @@ class _FusedClipLoss(torch.autograd.Function):
         if t_bf16 is None:
             t_bf16 = text_embeddings.detach().to(torch.bfloat16).contiguous()
 
-        if world > 1:
-            t_all_bf16 = _all_gather_rows(t_bf16, group, world)
-        else:
-            t_all_bf16 = t_bf16
-        shift_rows = -rank * n_loc  # delta_ij = 1 iff i_loc == j_glob - rank*b
-
-        # rows of S owned by the local images: complete after one sweep over T_all
-        r_max_p, r_l_p, r_diag = lse_stats(i_bf16, t_all_bf16, scale, shift_rows)
-        r_max, r_lg, r_q, r_loss, _ = merge_stats(r_max_p, r_l_p, r_diag, scale)
-        # columns (= rows of S^T owned by the texts): partial over the local images
-        lo = rank * n_loc
-        c_max_p, c_l_p, c_diag = lse_stats(t_all_bf16, i_bf16, scale, lo)
-        if world > 1:
-            c_max_p = _all_gather_rows(c_max_p.unsqueeze(0), group, world)
-            c_l_p = _all_gather_rows(c_l_p.unsqueeze(0), group, world)
-            c_diag = _all_gather_rows(c_diag[lo:lo + n_loc], group, world)
-        c_max, c_lg, c_q, c_loss, _ = merge_stats(c_max_p, c_l_p, c_diag, scale)
-        sums = _loss_sums(r_loss, c_loss[lo:lo + n_loc])
-        if world > 1:
-            _dist().all_reduce(sums, group=group)
-        losses = sums / float(n_glob)
-        image_loss = losses[0]
-        text_loss = losses[1]
-        loss = (image_loss + text_loss) * 0.5                      # reference :552
-
+        plan = sharded.forward_plan(CudaOps, i_bf16, t_bf16, scale, group)
+        world = plan["world"]
         ctx.group = group
-        ctx.world, ctx.rank = world, rank
-        ctx.n_loc, ctx.n_glob = n_loc, n_glob
+        ctx.world, ctx.rank = world, plan["rank"]
+        ctx.n_loc, ctx.n_glob = n_loc, plan["n_glob"]
         ctx.scale, ctx.exp_ls, ctx.clamped = scale, e, clamped
         ctx.grad_scale = float(grad_scale)
         ctx.in_dtypes = (image_embeddings.dtype, text_embeddings.dtype, logit_scale.dtype)
         ctx.ls_shape = logit_scale.shape
-        ctx.save_for_backward(i_bf16, t_all_bf16, r_max, r_lg, r_q, c_max, c_lg, c_q)
+        ctx.save_for_backward(i_bf16, plan["t_all"], *plan["r_stats"], *plan["c_stats"])
         ctx.f16 = (i_f16, t_f16 if world == 1 else None)
-        return loss, image_loss, text_loss
+        return plan["loss"], plan["image_loss"], plan["text_loss"]
 
     @staticmethod
     def backward(ctx, g_loss, g_il, g_tl):
@@ -267,30 +247,15 @@ class _FusedClipLoss(torch.autograd.Function):
 
         i_f16, t_f16 = ctx.f16
         if i_f16 is None:
-            i_f16 = cast_bf16_to_f16(i_bf16)
-        t_all_f16 = t_f16 if t_f16 is not None else cast_bf16_to_f16(t_all_bf16)
-        n_loc, n_glob, rank, world = ctx.n_loc, ctx.n_glob, ctx.rank, ctx.world
-        scale = ctx.scale
+            i_f16 = CudaOps.to_backward_operand(i_bf16)
+        t_all_f16 = t_f16 if t_f16 is not None else CudaOps.to_backward_operand(t_all_bf16)
+        world = ctx.world
         gs = ctx.grad_scale
-
-        d_i = d_t = d_ls = None
-        ds = None
-        if need_i or need_ls:
-            d_i, ds = _grad(i_f16, t_all_f16, r_stats, c_stats, scale, -rank * n_loc, n_glob,
-                            w_r, w_c, want_dscale=need_ls)
-        if need_t:
-            d_t_all, ds_t = _grad(t_all_f16, i_f16, c_stats, r_stats, scale, rank * n_loc,
-                                  n_glob, w_c, w_r, want_dscale=(need_ls and ds is None))
-            if ds is None:
-                ds = ds_t
-            if world > 1:
-                d_t = torch.empty(n_loc, d_t_all.shape[1], dtype=torch.float32, device=d_t_all.device)
-                _dist().reduce_scatter_tensor(d_t, d_t_all, group=ctx.group)
-            else:
-                d_t = d_t_all
+        d_i, d_t, ds = sharded.backward_plan(
+            CudaOps, i_f16, t_all_f16, r_stats, c_stats, ctx.scale, ctx.n_loc, ctx.n_glob, ctx.rank,
+            world, ctx.group, w_r, w_c, need_i, need_t, need_ls)
+        d_ls = None
         if need_ls:
-            if world > 1:
-                _dist().all_reduce(ds, group=ctx.group)
             # d/dl clamp(e^l, max=100) = e^l if e^l <= 100 else 0   (reference :456-457)
             d_ls = ds * (0.0 if ctx.clamped else ctx.exp_ls)
             d_ls = (d_ls * mul * gs).to(ctx.in_dtypes[2]).reshape(ctx.ls_shape)

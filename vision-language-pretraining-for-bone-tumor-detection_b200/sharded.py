@@ -1,0 +1,102 @@
+"""Host-side plan of the (optionally row-sharded) fused CLIP loss.
+
+One process per GPU; rank r owns rows [r*b, (r+1)*b) of both embedding streams (b = N / world).
+The plan is written against a small ``ops`` interface so that the very same collective
+orchestration runs (a) in production on the CUDA kernels (``functional.CudaOps``) and (b) in the
+CPU test-suite on a numpy restatement of the kernel contracts under the ``gloo`` backend
+(``tests/test_distributed_cpu.py``).  Only the per-rank tile work differs; the exchange steps are:
+
+forward   all_gather(T_loc)                       -> T_all            (b*D bf16 per rank)
+          all_gather(col (max, l) partials, diag) -> column statistics (3 * N fp32 per rank)
+          all_reduce([sum row_loss, sum col_loss])                     (2 fp32)
+backward  reduce_scatter(dT_all partial)          -> dT_loc           (N*D fp32 per rank)
+          all_reduce(dscale)                                           (1 fp32)
+
+``ops`` contract (shapes: x [n_rows, D], y [n_cols, D]):
+    lse_stats(x, y, scale, diag_shift) -> (row_max, row_l, diag)
+        row_max[i] = max_j <x_i, y_j> (positive pair included), row_l[i] = sum over j != positive
+        of exp(scale*<x_i,y_j> - scale*row_max[i]) (up to the fp32 rounding the merge undoes),
+        diag[i] = <x_i, y_{i-diag_shift}> or 0 when that column does not exist.
+    merge_stats(part_max [P,n], part_l [P,n], diag [n], scale) -> (max, lg2l, q, row_loss)
+    loss_sums(row_loss, col_loss) -> 2-vector
+    grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale) -> (dx, ds)
+    to_backward_operand(x) -> operand copy used by grad (fp16 on the GPU)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def group_info(group):
+    if group is None:
+        return 1, 0
+    dist = _dist()
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def all_gather_rows(t: torch.Tensor, group, world: int) -> torch.Tensor:
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    _dist().all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+def forward_plan(ops, i_loc, t_loc, scale: float, group=None):
+    """Returns a dict with the three losses (device scalars) and everything backward needs."""
+    world, rank = group_info(group)
+    n_loc = i_loc.shape[0]
+    n_glob = n_loc * world
+    lo = rank * n_loc
+    t_all = all_gather_rows(t_loc, group, world) if world > 1 else t_loc
+
+    # rows of S owned by the local images: complete after one sweep over T_all
+    r_max_p, r_l_p, r_diag = ops.lse_stats(i_loc, t_all, scale, -lo)
+    r_max, r_lg, r_q, r_loss = ops.merge_stats(r_max_p, r_l_p, r_diag, scale)
+    # columns (= rows of S^T owned by the texts): partial over the local images
+    c_max_p, c_l_p, c_diag = ops.lse_stats(t_all, i_loc, scale, lo)
+    if world > 1:
+        c_max_p = all_gather_rows(c_max_p.unsqueeze(0), group, world)
+        c_l_p = all_gather_rows(c_l_p.unsqueeze(0), group, world)
+        c_diag = all_gather_rows(c_diag[lo:lo + n_loc], group, world)
+    c_max, c_lg, c_q, c_loss = ops.merge_stats(c_max_p, c_l_p, c_diag, scale)
+    sums = ops.loss_sums(r_loss, c_loss[lo:lo + n_loc])
+    if world > 1:
+        _dist().all_reduce(sums, group=group)
+    losses = sums / float(n_glob)
+    return {"image_loss": losses[0], "text_loss": losses[1],
+            "loss": (losses[0] + losses[1]) * 0.5,            # reference :552
+            "t_all": t_all, "r_stats": (r_max, r_lg, r_q), "c_stats": (c_max, c_lg, c_q),
+            "world": world, "rank": rank, "n_loc": n_loc, "n_glob": n_glob}
+
+
+def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc: int, n_glob: int,
+                  rank: int, world: int, group=None, w_row: float = 1.0, w_col: float = 1.0,
+                  need_i: bool = True, need_t: bool = True, need_scale: bool = True):
+    """(dI_loc, dT_loc, dscale) of the global loss; operands are the backward copies."""
+    lo = rank * n_loc
+    d_i = d_t = ds = None
+    if need_i or need_scale:
+        d_i, ds = ops.grad(i_loc_op, t_all_op, r_stats, c_stats, scale, -lo, n_glob, w_row, w_col,
+                           need_scale)
+        if not need_i:
+            d_i = None
+    if need_t:
+        d_t_all, ds_t = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col, w_row,
+                                 need_scale and ds is None)
+        if ds is None:
+            ds = ds_t
+        if world > 1:
+            d_t = torch.empty((n_loc,) + tuple(d_t_all.shape[1:]), dtype=d_t_all.dtype,
+                              device=d_t_all.device)
+            _dist().reduce_scatter_tensor(d_t, d_t_all.contiguous(), group=group)
+        else:
+            d_t = d_t_all
+    if need_scale and world > 1:
+        _dist().all_reduce(ds, group=group)
+    return d_i, d_t, ds
