@@ -51,8 +51,8 @@ struct GradParams {
   int diag_shift;
   float scale_log2;
   float out_scale;      // scale / (2 n_global) / 2^13
-  float* dx;            // [n_rows, d]
-  int use_atomics;      // n_chunks > 1
+  float* dx;            // [n_rows, d] (n_chunks == 1) or per-chunk partials [n_chunks][n_rows, d]
+  size_t chunk_stride;  // elements between the partial buffers of consecutive chunks
   float* ds_part;       // [n_items * 8] or nullptr
 };
 
@@ -404,28 +404,23 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         const int row = rb * 128 + row_in_blk;
         mbar_wait(smem_u32(&bars->acc_full), item_ctr & 1);
         tc_fence_after();
-        float* orow = p.dx + (size_t)row * p.d;
+        const int chunk = item / p.n_row_blocks;
+        float* orow = p.dx + (size_t)chunk * p.chunk_stride + (size_t)(row < p.n_rows ? row : 0) * p.d;
         for (int c = 0; c < p.kblocks * 64; c += 32) {
           uint32_t v[32];
           tmem_ld_x32(tmem + lane_addr + c, v);
           tmem_ld_wait();
           if (row < p.n_rows) {
-            if (p.use_atomics) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c + j < p.d) atomicAdd(orow + c + j, __uint_as_float(v[j]) * p.out_scale);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (c + j < p.d) {
-                  float4 o;
-                  o.x = __uint_as_float(v[j + 0]) * p.out_scale;
-                  o.y = __uint_as_float(v[j + 1]) * p.out_scale;
-                  o.z = __uint_as_float(v[j + 2]) * p.out_scale;
-                  o.w = __uint_as_float(v[j + 3]) * p.out_scale;
-                  *reinterpret_cast<float4*>(orow + c + j) = o;
-                }
-            }
+            for (int j = 0; j < 32; j += 4)
+              if (c + j < p.d) {
+                float4 o;
+                o.x = __uint_as_float(v[j + 0]) * p.out_scale;
+                o.y = __uint_as_float(v[j + 1]) * p.out_scale;
+                o.z = __uint_as_float(v[j + 2]) * p.out_scale;
+                o.w = __uint_as_float(v[j + 3]) * p.out_scale;
+                *reinterpret_cast<float4*>(orow + c + j) = o;
+              }
           }
         }
         tc_fence_before();
@@ -450,6 +445,24 @@ __global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __re
   if (i < n_pad) {
     mx_out[i] = i < n ? mx[i] : 0.f;
     lg_out[i] = i < n ? lg[i] - log2w : INFINITY;
+  }
+}
+
+// dx = sum over chunks of the per-chunk partial blocks, fixed order (bit reproducible)
+__global__ void dx_reduce_kernel(const float4* __restrict__ part, size_t chunk_stride4, int n_chunks,
+                                 size_t n4, float4* __restrict__ dx) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 a = part[i];
+    for (int c = 1; c < n_chunks; ++c) {
+      const float4 b = part[(size_t)c * chunk_stride4 + i];
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    dx[i] = a;
   }
 }
 
@@ -491,9 +504,18 @@ static void pick_chunks_pairs(int n_row_blocks, int total_tiles, int n_pairs, in
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-static size_t grad_ws_bytes(int n_rows, int n_cols) {
+static int n_pairs_of_device() {
+  const int n = sm_count();
+  return n > 1 ? n / 2 : 74;   // no device (host-side size queries): assume a B200
+}
+
+static size_t grad_ws_bytes(int n_rows, int n_cols, int d) {
   const size_t nrb = (n_rows + 127) / 128, nt = (n_cols + 127) / 128;
-  return 2 * align256(nrb * 128 * 4) + 2 * align256(nt * 128 * 4) + align256(nrb * 16 * 8 * 4) + 256;
+  int n_chunks, tpc;
+  pick_chunks_pairs((int)nrb, (int)nt, n_pairs_of_device(), &n_chunks, &tpc);
+  const size_t partials = n_chunks > 1 ? align256((size_t)n_chunks * n_rows * d * 4) : 0;
+  return 2 * align256(nrb * 128 * 4) + 2 * align256(nt * 128 * 4) + align256(nrb * 16 * 8 * 4) +
+         partials + 256;
 }
 
 }  // namespace vlp
@@ -503,9 +525,8 @@ using namespace vlp;
 extern "C" {
 
 size_t vlpclip_grad_workspace_bytes(int n_rows, int n_cols, int d) {
-  (void)d;
-  if (n_rows <= 0 || n_cols <= 0) return 0;
-  return grad_ws_bytes(n_rows, n_cols);
+  if (n_rows <= 0 || n_cols <= 0 || d <= 0) return 0;
+  return grad_ws_bytes(n_rows, n_cols, d);
 }
 
 int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_max,
@@ -528,9 +549,9 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
     return fail(-1, "grad: direction weights must be >= 0 and not both zero");
   int rc = check_device_sm100();
   if (rc) return rc;
-  if (workspace_bytes < grad_ws_bytes(n_rows, n_cols))
+  if (workspace_bytes < grad_ws_bytes(n_rows, n_cols, d))
     return fail(-1, "grad: workspace too small (%zu < %zu)", workspace_bytes,
-                grad_ws_bytes(n_rows, n_cols));
+                grad_ws_bytes(n_rows, n_cols, d));
 
   GradParams p;
   p.x = (const __half*)x;
@@ -541,7 +562,7 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   p.kblocks = (d + 63) / 64;
   p.total_tiles = (n_cols + 127) / 128;
   p.n_row_blocks = (n_rows + 127) / 128;
-  const int n_pairs = sm_count() / 2;
+  const int n_pairs = n_pairs_of_device();
   pick_chunks_pairs(p.n_row_blocks, p.total_tiles, n_pairs, &p.n_chunks, &p.tiles_per_chunk);
   p.diag_shift = diag_shift;
   p.scale_log2 = scale * kLog2e;
@@ -550,8 +571,6 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   p.xq = x_q;
   p.yq = y_q;
   p.out_scale = scale / (2.0f * (float)n_global) / G_SCALE;
-  p.dx = dx;
-  p.use_atomics = p.n_chunks > 1;
 
   uint8_t* ws = (uint8_t*)workspace;
   const int npx = p.n_row_blocks * 128, npy = p.total_tiles * 128;
@@ -564,6 +583,10 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   float* ylg = (float*)ws;
   ws += align256((size_t)npy * 4);
   float* ds_part = (float*)ws;
+  ws += align256((size_t)p.n_row_blocks * 16 * 8 * 4);
+  float* dx_part = (float*)ws;
+  p.dx = p.n_chunks > 1 ? dx_part : dx;
+  p.chunk_stride = (size_t)n_rows * d;
   p.xmax = xmax;
   p.xlg = xlg;
   p.ymax = ymax;
@@ -576,7 +599,6 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
                                                           log2f(w_col), ymax, ylg);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
-  if (p.use_atomics) VLP_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)n_rows * d * sizeof(float), stream));
 
   CUtensorMap map_k, map_mn;
   rc = make_tmap_sw128(&map_k, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
@@ -596,6 +618,15 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   grad_pair_kernel<<<clusters * 2, BWD_THREADS, smem, stream>>>(map_k, map_mn, p);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
+  if (p.n_chunks > 1) {
+    const size_t n4 = (size_t)n_rows * d / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    dx_reduce_kernel<<<blocks, 256, 0, stream>>>((const float4*)dx_part, n4, p.n_chunks, n4,
+                                                 (float4*)dx);
+    VLP_COUNT_LAUNCH(1);
+    VLP_CUDA_OK(cudaGetLastError());
+  }
   if (dscale) {
     ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, n_items * 8, 1.0f / (2.0f * (float)n_global),
                                             dscale);
