@@ -25,8 +25,10 @@
 namespace vlp {
 
 constexpr int BWD_THREADS = 320;
-constexpr int P_STAGES = 8;                 // producer ring: [128 q x 64 k] fp16 = 16 KB
-constexpr int P_STAGE_BYTES = 16384;
+constexpr int P_KB_PER_STAGE = 2;           // producer ring stage: 2 boxes of [128 q x 64 k] fp16
+constexpr int P_BOX_BYTES = 16384;
+constexpr int P_STAGE_BYTES = P_KB_PER_STAGE * P_BOX_BYTES;
+constexpr int P_STAGES = 4;
 constexpr int C_STAGES = 4;                 // consumer ring: [64 q x 256 d] fp16 = 32 KB
 constexpr int C_STAGE_BYTES = 32768;
 constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
@@ -158,54 +160,63 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     // producer CTA: S tiles + softmax -> G tiles pushed to the peer
     // =====================================================================================
     if (warp == 0) {
-      if (lane == 0) {
-        uint32_t it = 0;
-        for (int item = cluster_id; item < n_items; item += n_clusters) {
-          const int chunk = item / p.n_row_blocks;
-          const int t0 = chunk * p.tiles_per_chunk;
-          const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-          for (int t = t0; t < t1; ++t)
-            for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-              const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
-              mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
-              mbar_expect_tx(smem_u32(&bars->full[st]), P_STAGE_BYTES);
-              tma_load_2d(ring + st * P_STAGE_BYTES, &map_y_k, smem_u32(&bars->full[st]), kb * 64,
-                          t * 128);
+      uint32_t it = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int chunk = item / p.n_row_blocks;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t)
+          for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
+            const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
+            const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
+            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(smem_u32(&bars->full[st]), nkb * P_BOX_BYTES);
+              for (int q = 0; q < nkb; ++q)
+                tma_load_2d(ring + st * P_STAGE_BYTES + q * P_BOX_BYTES, &map_y_k,
+                            smem_u32(&bars->full[st]), (kb + q) * 64, t * 128);
             }
-        }
+            __syncwarp();
+          }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_K, 128, 128);
-        uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
-        for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
-          const int chunk = item / p.n_row_blocks;
-          const int t0 = chunk * p.tiles_per_chunk;
-          const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-          mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+      const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_K, 128, 128);
+      uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
+        const int chunk = item / p.n_row_blocks;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+        tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++tile_ctr) {
+          const uint32_t buf = tile_ctr & 1;
+          mbar_wait(smem_u32(&bars->s_empty[buf]), ((tile_ctr >> 1) & 1) ^ 1);
           tc_fence_after();
-          for (int t = t0; t < t1; ++t, ++tile_ctr) {
-            const uint32_t buf = tile_ctr & 1;
-            mbar_wait(smem_u32(&bars->s_empty[buf]), ((tile_ctr >> 1) & 1) ^ 1);
+          const uint32_t d_tmem = tmem + BWD_TMEM_S + buf * 128;
+          for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
+            const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
+            const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
+            mbar_wait(smem_u32(&bars->full[st]), ph);
             tc_fence_after();
-            const uint32_t d_tmem = tmem + BWD_TMEM_S + buf * 128;
-            for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-              const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
-              mbar_wait(smem_u32(&bars->full[st]), ph);
-              tc_fence_after();
-              const uint32_t sb = ring + st * P_STAGE_BYTES;
+            if (elect_one()) {
+              for (int q = 0; q < nkb; ++q) {
+                const uint32_t sb = ring + st * P_STAGE_BYTES + q * P_BOX_BYTES;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_ts<1>(d_tmem, tmem + BWD_TMEM_X + kb * 32 + ks * 8,
-                           make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | ks) != 0);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ts<1>(d_tmem, tmem + BWD_TMEM_X + (kb + q) * 32 + ks * 8,
+                             make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | q | ks) != 0);
+              }
               umma_commit<1>(smem_u32(&bars->empty[st]));
             }
-            umma_commit<1>(smem_u32(&bars->s_full[buf]));
+            __syncwarp();
           }
-          umma_commit<1>(smem_u32(&bars->x_free));
+          if (elect_one()) umma_commit<1>(smem_u32(&bars->s_full[buf]));
+          __syncwarp();
         }
-        if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+        if (elect_one()) umma_commit<1>(smem_u32(&bars->x_free));
+        __syncwarp();
       }
+      if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
     } else {
       // ---- softmax warps ----
       const uint32_t quarter = warp & 3;
@@ -333,50 +344,50 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     // =====================================================================================
     const int n_nc = (p.kblocks + 3) / 4;  // 256-wide accumulator chunks
     if (warp == 0) {
-      if (lane == 0) {
-        uint32_t it = 0;
-        for (int item = cluster_id; item < n_items; item += n_clusters) {
-          const int chunk = item / p.n_row_blocks;
-          const int t0 = chunk * p.tiles_per_chunk;
-          const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-          for (int t = t0; t < t1; ++t)
-            for (int nc = 0; nc < n_nc; ++nc) {
-              const int nb = min(4, p.kblocks - nc * 4);
-              for (int kh = 0; kh < 2; ++kh, ++it) {
-                const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
-                mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      uint32_t it = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters) {
+        const int chunk = item / p.n_row_blocks;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        for (int t = t0; t < t1; ++t)
+          for (int nc = 0; nc < n_nc; ++nc) {
+            const int nb = min(4, p.kblocks - nc * 4);
+            for (int kh = 0; kh < 2; ++kh, ++it) {
+              const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
+              mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+              if (elect_one()) {
                 mbar_expect_tx(smem_u32(&bars->full[st]), nb * 8192);
                 for (int b = 0; b < nb; ++b)
                   tma_load_2d(ring + st * C_STAGE_BYTES + b * 8192, &map_y_mn,
                               smem_u32(&bars->full[st]), (nc * 4 + b) * 64, t * 128 + kh * 64);
               }
+              __syncwarp();
             }
-        }
+          }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
-        for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
-          const int chunk = item / p.n_row_blocks;
-          const int t0 = chunk * p.tiles_per_chunk;
-          const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-          if (item_ctr > 0) {
-            mbar_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1);
-            tc_fence_after();
-          }
-          for (int t = t0; t < t1; ++t, ++tile_ctr) {
-            const uint32_t slot = tile_ctr & 1;
-            mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1);
-            tc_fence_after();
-            const uint32_t ga = gslots + slot * G_SLOT_BYTES;
-            for (int nc = 0; nc < n_nc; ++nc) {
-              const int nb = min(4, p.kblocks - nc * 4);
-              const uint32_t idesc =
-                  make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
-              for (int kh = 0; kh < 2; ++kh, ++it) {
-                const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
-                mbar_wait(smem_u32(&bars->full[st]), ph);
-                tc_fence_after();
+      uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
+        const int chunk = item / p.n_row_blocks;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        if (item_ctr > 0) {
+          mbar_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1);
+          tc_fence_after();
+        }
+        for (int t = t0; t < t1; ++t, ++tile_ctr) {
+          const uint32_t slot = tile_ctr & 1;
+          mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1);
+          tc_fence_after();
+          const uint32_t ga = gslots + slot * G_SLOT_BYTES;
+          for (int nc = 0; nc < n_nc; ++nc) {
+            const int nb = min(4, p.kblocks - nc * 4);
+            const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
+            for (int kh = 0; kh < 2; ++kh, ++it) {
+              const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
+              mbar_wait(smem_u32(&bars->full[st]), ph);
+              tc_fence_after();
+              if (elect_one()) {
                 const uint32_t sb = ring + st * C_STAGE_BYTES;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -386,12 +397,15 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
                 }
                 umma_commit<1>(smem_u32(&bars->empty[st]));
               }
+              __syncwarp();
             }
-            // release the G slot in the producer CTA (rank 0)
-            umma_commit_mcast<1>(smem_u32(&bars->g_empty[slot]), 0x1);
           }
-          umma_commit<1>(smem_u32(&bars->acc_full));
+          // release the G slot in the producer CTA (rank 0)
+          if (elect_one()) umma_commit_mcast<1>(smem_u32(&bars->g_empty[slot]), 0x1);
+          __syncwarp();
         }
+        if (elect_one()) umma_commit<1>(smem_u32(&bars->acc_full));
+        __syncwarp();
       }
     } else if (warp < 6) {
       // ---- epilogue: TMEM accumulator -> global ----

@@ -21,8 +21,10 @@
 
 namespace vlp {
 
-constexpr int FWD_STAGES = 8;
-constexpr int FWD_STAGE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+constexpr int FWD_KB_PER_STAGE = 2;          // k-blocks (128 rows x 64 bf16 = 16 KB boxes) per stage
+constexpr int FWD_BOX_BYTES = 128 * 128;
+constexpr int FWD_STAGE_BYTES = FWD_KB_PER_STAGE * FWD_BOX_BYTES;
+constexpr int FWD_STAGES = 6;
 constexpr int FWD_THREADS = 320;
 constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: up to 256 columns (d <= 512)
 constexpr uint32_t TMEM_S_COL = 256;    // two S buffers of 128 columns
@@ -87,61 +89,70 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
   const int n_items = p.n_row_blocks * p.n_chunks;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      uint32_t it = 0;  // running stage counter
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int chunk = item / p.n_row_blocks;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-        for (int t = t0; t < t1; ++t) {
-          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-            const uint32_t st = it % FWD_STAGES;
-            const uint32_t ph = (it / FWD_STAGES) & 1;
-            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
-            mbar_expect_tx(smem_u32(&bars->full[st]), FWD_STAGE_BYTES);
-            tma_load_2d(ring + st * FWD_STAGE_BYTES, &map_y, smem_u32(&bars->full[st]), kb * 64,
-                        t * 128);
+    // ================= TMA producer (whole warp converged, one elected lane issues) ==========
+    uint32_t it = 0;  // running stage counter
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int chunk = item / p.n_row_blocks;
+      const int t0 = chunk * p.tiles_per_chunk;
+      const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE, ++it) {
+          const uint32_t st = it % FWD_STAGES;
+          const uint32_t ph = (it / FWD_STAGES) & 1;
+          const int nkb = min(FWD_KB_PER_STAGE, p.kblocks - kb);
+          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(smem_u32(&bars->full[st]), nkb * FWD_BOX_BYTES);
+            for (int q = 0; q < nkb; ++q)
+              tma_load_2d(ring + st * FWD_STAGE_BYTES + q * FWD_BOX_BYTES, &map_y,
+                          smem_u32(&bars->full[st]), (kb + q) * 64, t * 128);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, MAJOR_K, MAJOR_K, 128, 128);
-      uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
-        const int chunk = item / p.n_row_blocks;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-        mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+    // ================= MMA issuer (whole warp converged, one elected lane issues) ===========
+    const uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, MAJOR_K, MAJOR_K, 128, 128);
+    uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
+      const int chunk = item / p.n_row_blocks;
+      const int t0 = chunk * p.tiles_per_chunk;
+      const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+      tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++tile_ctr) {
+        const uint32_t buf = tile_ctr & 1;
+        mbar_wait(smem_u32(&bars->s_empty[buf]), ((tile_ctr >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int t = t0; t < t1; ++t, ++tile_ctr) {
-          const uint32_t buf = tile_ctr & 1;
-          mbar_wait(smem_u32(&bars->s_empty[buf]), ((tile_ctr >> 1) & 1) ^ 1);
+        const uint32_t d_tmem = tmem + TMEM_S_COL + buf * 128;
+        for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE, ++it) {
+          const uint32_t st = it % FWD_STAGES;
+          const uint32_t ph = (it / FWD_STAGES) & 1;
+          const int nkb = min(FWD_KB_PER_STAGE, p.kblocks - kb);
+          mbar_wait(smem_u32(&bars->full[st]), ph);
           tc_fence_after();
-          const uint32_t d_tmem = tmem + TMEM_S_COL + buf * 128;
-          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-            const uint32_t st = it % FWD_STAGES;
-            const uint32_t ph = (it / FWD_STAGES) & 1;
-            mbar_wait(smem_u32(&bars->full[st]), ph);
-            tc_fence_after();
-            const uint32_t sb = ring + st * FWD_STAGE_BYTES;
+          if (elect_one()) {
+            for (int q = 0; q < nkb; ++q) {
+              const uint32_t sb = ring + st * FWD_STAGE_BYTES + q * FWD_BOX_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_ts<1>(d_tmem, tmem + TMEM_X_COL + kb * 32 + ks * 8,
-                         make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | ks) != 0);
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_ts<1>(d_tmem, tmem + TMEM_X_COL + (kb + q) * 32 + ks * 8,
+                           make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | q | ks) != 0);
+              }
             }
             umma_commit<1>(smem_u32(&bars->empty[st]));
           }
-          umma_commit<1>(smem_u32(&bars->s_full[buf]));
+          __syncwarp();
         }
-        umma_commit<1>(smem_u32(&bars->x_free));
+        if (elect_one()) umma_commit<1>(smem_u32(&bars->s_full[buf]));
+        __syncwarp();
       }
-      // do not exit with an arrive still in flight
-      if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+      if (elect_one()) umma_commit<1>(smem_u32(&bars->x_free));
+      __syncwarp();
     }
+    // do not exit with an arrive still in flight
+    if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
   } else {
     // ================= softmax warps =================
     const uint32_t quarter = warp & 3;           // TMEM lane quarter this warp may touch
