@@ -222,3 +222,19 @@ def test_permutation_equivariance(VF):
     b = run_fused(VF, I[perm], T[perm], 2.6593)
     assert abs(a["loss"] - b["loss"]) < 1e-5 * a["loss"]
     assert O.rel_err(b["dI"], a["dI"][perm.numpy()]) < 2e-4
+
+
+def test_wide_lse_spread_takes_the_two_exp_path(VF):
+    """Half of the pairs perfectly aligned (LSE ~ s), the other half unrelated (LSE ~ 0.3 s) at the
+    clamped temperature: the global log2-LSE spread exceeds the single-ex2 guard of the backward,
+    which must fall back to two ex2 per logit and stay within tolerance."""
+    n, d, ls = 384, 64, 5.0
+    g = torch.Generator().manual_seed(11)
+    I = torch.nn.functional.normalize(torch.randn(n, d, generator=g)).to(torch.bfloat16).float()
+    T = I.clone()
+    T[n // 2:] = torch.nn.functional.normalize(torch.randn(n - n // 2, d, generator=g)).to(torch.bfloat16).float()
+    ref = O.closed_form(I.numpy(), T.numpy(), ls)
+    spread = (ref["row_lse"].max() - ref["row_lse"].min()) * math.log2(math.e)
+    assert spread > 60.0
+    got = run_fused(VF, I, T, ls)
+    assert_close(got, ref, ref["dlogit_scale"])

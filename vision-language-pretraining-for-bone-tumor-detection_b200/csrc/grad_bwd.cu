@@ -45,6 +45,9 @@ struct GradParams {
   const float* xlg;     // [n_row_blocks*128] log2(sum) - k*max of X rows (+inf padded)
   const float* ymax;    // [total_tiles*128]  same for the rows of Y
   const float* ylg;
+  const float* xr;      // [n_row_blocks*128] 2^(lse2_x - C)  (fast path; 0 for padded rows)
+  const float* yc;      // [total_tiles*128]  2^(C - lse2_y)  (fast path; 0 for padded rows)
+  const int* fast_flag; // 1: global LSE spread small enough for the single-ex2 path
   const float* xq;      // [n_rows] 1 - P_row(positive)   (unpadded, read only on the diagonal)
   const float* yq;      // [n_cols] 1 - P_col(positive)
   float w_row, w_col;
@@ -103,6 +106,37 @@ __device__ __forceinline__ void softmax_tile(const uint32_t (&v)[64],
       if (kDiag) gg = (j == diag_j) ? diag_val : gg;  // = -(w_r (1-P_row) + w_c (1-P_col))
       ds_acc = fmaf(gg, s, ds_acc);
       g[e] = gg * G_SCALE;
+    }
+    out[q * 2 + 0] = pack_f16x2(g[0], g[1]);
+    out[q * 2 + 1] = pack_f16x2(g[2], g[3]);
+  }
+}
+
+// Single-ex2 variant: with a = w_row P_row 2^13 = 2^(k (s - xmax_i) - xlg_i + 13) the column
+// term is a * 2^(lse2_x_i - lse2_y_j) = a * xr_i * yc_j (xr, yc precomputed around the global
+// midpoint C of all LSEs).  Valid while every |lse2_x_i - lse2_y_j| stays far from the fp32
+// exponent range; the prep kernel checks the global spread and sets fast_flag accordingly.
+// Halves the MUFU work, which bounds this kernel (16 ex2 / clk / SM).
+template <bool kDiag>
+__device__ __forceinline__ void softmax_tile_fast(const uint32_t (&v)[64],
+                                                  const float4* __restrict__ yc4, float xmax,
+                                                  float xlg13, float xr, float scale_log2,
+                                                  float diag_val_scaled, int diag_j,
+                                                  uint32_t (&out)[32], float& ds_acc) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float4 yc = __ldg(yc4 + q);
+    const float ycv[4] = {yc.x, yc.y, yc.z, yc.w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q * 4 + e;
+      const float s = __uint_as_float(v[j]);
+      const float a = ex2_approx(fmaf(s - xmax, scale_log2, -xlg13));
+      float gg = fmaf(a, xr * ycv[e], a);
+      if (kDiag) gg = (j == diag_j) ? diag_val_scaled : gg;
+      ds_acc = fmaf(gg, s, ds_acc);
+      g[e] = gg;
     }
     out[q * 2 + 0] = pack_f16x2(g[0], g[1]);
     out[q * 2 + 1] = pack_f16x2(g[2], g[3]);
@@ -262,6 +296,8 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         }
         const float xmax = p.xmax[row];  // padded to n_row_blocks*128
         const float xlg = p.xlg[row];
+        const float xr = p.xr[row];
+        const bool fast = *p.fast_flag != 0;
         const int dcol = row_ok ? row - p.diag_shift : -1000000000;
         float ds_acc = 0.f;
 
@@ -288,9 +324,20 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           uint32_t out[32];
           const int diag_j = dcol - col0;
           const bool has_diag = diag_j >= 0 && diag_j < 64;
-          if (__any_sync(0xffffffffu, has_diag)) {
-            float diag_val = 0.f;
-            if (has_diag) diag_val = -(p.w_row * p.xq[row] + p.w_col * p.yq[dcol]);
+          const bool any_diag = __any_sync(0xffffffffu, has_diag);
+          float diag_val = 0.f;
+          if (has_diag) diag_val = -(p.w_row * p.xq[row] + p.w_col * p.yq[dcol]);
+          if (fast) {
+            const float4* yc4 = reinterpret_cast<const float4*>(p.yc + col0);
+            float acc = 0.f;   // carries the 2^13 tile scale
+            if (any_diag)
+              softmax_tile_fast<true>(v, yc4, xmax, xlg - 13.f, xr, p.scale_log2, diag_val * G_SCALE,
+                                      diag_j, out, acc);
+            else
+              softmax_tile_fast<false>(v, yc4, xmax, xlg - 13.f, xr, p.scale_log2, 0.f, diag_j, out,
+                                       acc);
+            ds_acc = fmaf(acc, 1.0f / G_SCALE, ds_acc);
+          } else if (any_diag) {
             softmax_tile<true>(v, ymax4, ylg4, xmax, xlg, p.scale_log2, diag_val, diag_j, out,
                                ds_acc);
           } else {
@@ -315,7 +362,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
             const uint32_t rbar = mapa_shared(smem_u32(&bars->g_full[slot]), 1);
             const uint32_t rdst = mapa_shared(gslots + slot * G_SLOT_BYTES, 1);
             asm volatile(
-                "mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
+                "mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
                     rbar),
                 "r"(G_SLOT_BYTES)
                 : "memory");
@@ -450,15 +497,57 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
 }
 
-// pad the per-row statistics to whole tiles: max -> 0, lg2l -> +inf (probability 0)
-// (a direction weight w >= 0 is folded in as lg2l - log2(w): w * 2^e = 2^(e + log2 w))
+// Global range of the log2-domain LSEs (rows of X and of Y, direction weights folded in):
+// out[0] = C (midpoint), flag = 1 when the spread allows the single-ex2 path.
+__global__ void lse_range_kernel(const float* __restrict__ xmax, const float* __restrict__ xlg,
+                                 int nx, float log2wx, const float* __restrict__ ymax,
+                                 const float* __restrict__ ylg, int ny, float log2wy,
+                                 float scale_log2, int force_slow, float* __restrict__ c_out,
+                                 int* __restrict__ flag) {
+  __shared__ float smin[1024], smax[1024];
+  float lo = INFINITY, hi = -INFINITY;
+  for (int i = threadIdx.x; i < nx + ny; i += blockDim.x) {
+    const float e = i < nx ? fmaf(scale_log2, xmax[i], xlg[i] - log2wx)
+                           : fmaf(scale_log2, ymax[i - nx], ylg[i - nx] - log2wy);
+    if (e == e && fabsf(e) != INFINITY) {   // a zero direction weight gives +inf: ignore
+      lo = fminf(lo, e);
+      hi = fmaxf(hi, e);
+    }
+  }
+  smin[threadIdx.x] = lo;
+  smax[threadIdx.x] = hi;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      smin[threadIdx.x] = fminf(smin[threadIdx.x], smin[threadIdx.x + s]);
+      smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float l = smin[0], h = smax[0];
+    // (a zero direction weight makes one factor of the factorisation vanish: use two ex2)
+    const bool ok = !force_slow && (h >= l) && (h - l) < 60.f;
+    c_out[0] = ok ? 0.5f * (l + h) : 0.f;
+    flag[0] = ok ? 1 : 0;
+  }
+}
+
+// pad the per-row statistics to whole tiles: max -> 0, lg2l -> +inf (probability 0); a direction
+// weight w >= 0 is folded in as lg2l - log2(w) (w * 2^e = 2^(e + log2 w)).  fac = 2^(sign*(e - C))
+// with e = k*max + lg2l is the fast-path row (sign +1) / column (sign -1) factor, 0 when padded.
 __global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __restrict__ lg, int n,
-                                 int n_pad, float log2w, float* __restrict__ mx_out,
-                                 float* __restrict__ lg_out) {
+                                 int n_pad, float log2w, float scale_log2, float sign,
+                                 const float* __restrict__ c_ptr, float* __restrict__ mx_out,
+                                 float* __restrict__ lg_out, float* __restrict__ fac_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) {
-    mx_out[i] = i < n ? mx[i] : 0.f;
-    lg_out[i] = i < n ? lg[i] - log2w : INFINITY;
+    const float m = i < n ? mx[i] : 0.f;
+    const float l = i < n ? lg[i] - log2w : INFINITY;
+    mx_out[i] = m;
+    lg_out[i] = l;
+    const float e = fmaf(scale_log2, m, l);
+    fac_out[i] = (i < n && fabsf(e) != INFINITY) ? exp2f(sign * (e - c_ptr[0])) : 0.f;
   }
 }
 
@@ -528,8 +617,8 @@ static size_t grad_ws_bytes(int n_rows, int n_cols, int d) {
   int n_chunks, tpc;
   pick_chunks_pairs((int)nrb, (int)nt, n_pairs_of_device(), &n_chunks, &tpc);
   const size_t partials = n_chunks > 1 ? align256((size_t)n_chunks * n_rows * d * 4) : 0;
-  return 2 * align256(nrb * 128 * 4) + 2 * align256(nt * 128 * 4) + align256(nrb * 16 * 8 * 4) +
-         partials + 256;
+  return 3 * align256(nrb * 128 * 4) + 3 * align256(nt * 128 * 4) + align256(nrb * 16 * 8 * 4) +
+         partials + 512;
 }
 
 }  // namespace vlp
@@ -596,6 +685,13 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   ws += align256((size_t)npy * 4);
   float* ylg = (float*)ws;
   ws += align256((size_t)npy * 4);
+  float* xr = (float*)ws;
+  ws += align256((size_t)npx * 4);
+  float* yc = (float*)ws;
+  ws += align256((size_t)npy * 4);
+  float* c_mid = (float*)ws;
+  int* fast_flag = (int*)(ws + 128);
+  ws += 256;
   float* ds_part = (float*)ws;
   ws += align256((size_t)p.n_row_blocks * 16 * 8 * 4);
   float* dx_part = (float*)ws;
@@ -605,12 +701,20 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   p.xlg = xlg;
   p.ymax = ymax;
   p.ylg = ylg;
+  p.xr = xr;
+  p.yc = yc;
+  p.fast_flag = fast_flag;
   p.ds_part = dscale ? ds_part : nullptr;
-  stats_pad_kernel<<<(npx + 255) / 256, 256, 0, stream>>>(x_max, x_lg2l, n_rows, npx,
-                                                          log2f(w_row), xmax, xlg);
+  const float l2wr = log2f(w_row), l2wc = log2f(w_col);
+  lse_range_kernel<<<1, 1024, 0, stream>>>(x_max, x_lg2l, n_rows, l2wr, y_max, y_lg2l, n_cols, l2wc,
+                                           p.scale_log2, (w_row == 0.f || w_col == 0.f) ? 1 : 0, c_mid,
+                                           fast_flag);
   VLP_COUNT_LAUNCH(1);
-  stats_pad_kernel<<<(npy + 255) / 256, 256, 0, stream>>>(y_max, y_lg2l, n_cols, npy,
-                                                          log2f(w_col), ymax, ylg);
+  stats_pad_kernel<<<(npx + 255) / 256, 256, 0, stream>>>(x_max, x_lg2l, n_rows, npx, l2wr,
+                                                          p.scale_log2, 1.f, c_mid, xmax, xlg, xr);
+  VLP_COUNT_LAUNCH(1);
+  stats_pad_kernel<<<(npy + 255) / 256, 256, 0, stream>>>(y_max, y_lg2l, n_cols, npy, l2wc,
+                                                          p.scale_log2, -1.f, c_mid, ymax, ylg, yc);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
 
