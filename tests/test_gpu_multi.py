@@ -1,0 +1,67 @@
+"""GPU, >= 2 devices, NCCL: the row-sharded fused loss (all-gather / stat merge / reduce-scatter)
+against the single-process fp64 oracle on the global batch (BASELINE config 3: 4096 x 512)."""
+import math
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, d, ls, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import vlp_b200  # noqa: F401
+        from vlp_b200 import functional as VF
+        from oracle import clip_oracle as O
+        I, T = O.make_embeddings(n, d, rho=0.35, seed=42)      # global batch built from the seed
+        b = n // world
+        Il = I[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+        Tl = T[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+        lsc = torch.tensor([ls], dtype=torch.float64, device=dev, requires_grad=True)
+        loss, il, tl = VF.fused_clip_loss_from_embeddings(Il, Tl, lsc, group=dist.group.WORLD)
+        loss.backward()
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss.item(), image_loss=il.item(),
+                 text_loss=tl.item(), dI=Il.grad.cpu().numpy(), dT=Tl.grad.cpu().numpy(),
+                 dl=lsc.grad.item())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,d,ls", [(2, 4096, 512, math.log(1 / 0.07)), (2, 600, 72, 3.0)])
+def test_sharded_global_batch_matches_oracle(tmp_path, world, n, d, ls):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    from oracle import clip_oracle as O
+    mp.spawn(_worker, args=(world, _free_port(), n, d, ls, str(tmp_path)), nprocs=world, join=True)
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=42)
+    ref = O.closed_form(I.numpy(), T.numpy(), ls)
+    b = n // world
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        assert abs(float(got["loss"]) - ref["loss"]) < 1e-4 * ref["loss"]
+        assert abs(float(got["image_loss"]) - ref["image_loss"]) < 1e-4 * ref["image_loss"]
+        assert O.rel_err(got["dI"], ref["dI"][r * b:(r + 1) * b]) < 1e-3
+        assert O.rel_err(got["dT"], ref["dT"][r * b:(r + 1) * b]) < 1e-3
+        assert abs(float(got["dl"]) - ref["dlogit_scale"]) < 1e-3 * abs(ref["dlogit_scale"])
