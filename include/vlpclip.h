@@ -58,6 +58,19 @@ int vlpclip_lse_fwd(const void* x_bf16, int ldx, const void* y_bf16, int ldy, in
                     int n_cols, int d, float scale, int diag_shift, float* row_max, float* row_l,
                     float* diag, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same sweep, but ALSO the statistics of the columns of S over the given rows (one pass over
+ * the logits instead of two): col_max[j] / col_l[j] ([n_cols] fp32) follow the (max, l) convention
+ * of the rows, except that col_max is an upper reference (>= the true column maximum) rather than
+ * the maximum itself; the positive pair (row j + diag_shift) is left out of col_l as well.
+ * Column partial sums are carried with 2^100 headroom: a term is dropped only if it lies more than
+ * 226 log2 units (157 nats) below the largest row maximum of its 32-row group.
+ * Replaces VisionLanguageModule.py:459 + the log-sum-exp halves of :550 AND :551. */
+size_t vlpclip_lse_fused_workspace_bytes(int n_rows, int n_cols, int d);
+int vlpclip_lse_fwd_fused(const void* x_bf16, int ldx, const void* y_bf16, int ldy, int n_rows,
+                          int n_cols, int d, float scale, int diag_shift, float* row_max,
+                          float* row_l, float* diag, float* col_max, float* col_l, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* merge `nparts` partial (max, l) pairs laid out [nparts][n] (fixed order) and fold the positive
  * pair logits `diag` [n] (may be NULL = no positive pair) back in.  Any output may be NULL:
  *   lse      natural-log LSE of the full row

@@ -23,6 +23,19 @@ class ContractOps:
         return row_max, e.sum(dim=1), diag
 
     @staticmethod
+    def lse_stats_fused(x, y, scale, diag_shift):
+        row_max, row_l, diag = ContractOps.lse_stats(x, y, scale, diag_shift)
+        c = x.double() @ y.double().T
+        n_rows, n_cols = c.shape
+        rows = torch.arange(n_rows)
+        dcol = rows - diag_shift
+        has = (dcol >= 0) & (dcol < n_cols)
+        col_ref = c.max(dim=0).values + 0.25            # any upper reference is allowed
+        e = torch.exp(scale * (c - col_ref[None, :]))
+        e[rows[has], dcol[has]] = 0.0
+        return row_max, row_l, diag, col_ref, e.sum(dim=0)
+
+    @staticmethod
     def merge_stats(part_max, part_l, diag, scale):
         if part_max.dim() == 1:
             part_max = part_max[None]; part_l = part_l[None]

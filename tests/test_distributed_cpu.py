@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, d, ls, out_dir):
+def _worker(rank, world, port, n, d, ls, out_dir, exact):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -38,7 +38,8 @@ def _worker(rank, world, port, n, d, ls, out_dir):
         i_loc = I[rank * b:(rank + 1) * b].double()
         t_loc = T[rank * b:(rank + 1) * b].double()
         scale = min(math.exp(ls), 100.0)
-        plan = sharded.forward_plan(ContractOps, i_loc, t_loc, scale, dist.group.WORLD)
+        plan = sharded.forward_plan(ContractOps, i_loc, t_loc, scale, dist.group.WORLD,
+                                    exact_columns=exact)
         d_i, d_t, ds = sharded.backward_plan(ContractOps, i_loc, plan["t_all"], plan["r_stats"],
                                              plan["c_stats"], scale, b, n, rank, world, dist.group.WORLD)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=plan["loss"].numpy(),
@@ -48,11 +49,12 @@ def _worker(rank, world, port, n, d, ls, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("world,n,d,ls", [(2, 96, 32, 2.6593), (4, 64, 16, 3.5), (2, 40, 24, 5.0)])
-def test_sharded_plan_matches_single_process_oracle(tmp_path, world, n, d, ls):
+def test_sharded_plan_matches_single_process_oracle(tmp_path, world, n, d, ls, exact):
     from oracle import clip_oracle as O
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, n, d, ls, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, d, ls, str(tmp_path), exact), nprocs=world, join=True)
     I, T = O.make_embeddings(n, d, rho=0.35, seed=42)
     ref = O.closed_form(I.numpy(), T.numpy(), ls)
     b = n // world

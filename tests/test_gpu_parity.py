@@ -238,3 +238,29 @@ def test_wide_lse_spread_takes_the_two_exp_path(VF):
     assert spread > 60.0
     got = run_fused(VF, I, T, ls)
     assert_close(got, ref, ref["dlogit_scale"])
+
+
+def test_fused_and_exact_column_statistics_agree(VF):
+    """vlpclip_lse_fwd_fused (one sweep) vs two vlpclip_lse_fwd sweeps, after the merge."""
+    dev = torch.device("cuda:0")
+    for (n_rows, n_cols, d, s, shift) in [(256, 256, 512, 14.29, 0), (300, 1000, 72, 50.0, 0),
+                                          (1024, 4096, 256, 100.0, -1024), (4096, 4096, 512, 100.0, 0)]:
+        n = max(n_rows, n_cols)
+        I, T = O.make_embeddings(n, d, rho=0.35, seed=3)
+        x = I[:n_rows].to(dev).to(torch.bfloat16).contiguous()
+        y = T[:n_cols].to(dev).to(torch.bfloat16).contiguous()
+        rm, rl, rd, cm, cl = VF.lse_stats_fused(x, y, s, shift)
+        rm2, rl2, rd2 = VF.lse_stats(x, y, s, shift)
+        cm2, cl2, cd2 = VF.lse_stats(y, x, s, -shift)
+        assert torch.equal(rm, rm2) and torch.equal(rd, rd2)
+        assert torch.allclose(rl, rl2, rtol=1e-6, atol=0)
+        # compare column LSEs (natural log) -- references differ, the totals must not
+        cdiag = torch.zeros(n_cols, device=dev)
+        idx = torch.arange(n_rows, device=dev) - shift
+        ok = (idx >= 0) & (idx < n_cols)
+        cdiag[idx[ok]] = rd[ok]
+        lse_f = VF.merge_stats(cm, cl, cdiag, s, want_lse=True)[4]
+        lse_e = VF.merge_stats(cm2, cl2, cd2, s, want_lse=True)[4]
+        has = torch.zeros(n_cols, dtype=torch.bool, device=dev)
+        has[idx[ok]] = True
+        assert torch.allclose(lse_f[has], lse_e[has], rtol=2e-6, atol=2e-5)

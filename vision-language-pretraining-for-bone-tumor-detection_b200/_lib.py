@@ -22,6 +22,10 @@ _SIGNATURES = {
     "vlpclip_lse_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlpclip_lse_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlpclip_lse_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "vlpclip_lse_fwd_fused": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
     "vlpclip_lse_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlpclip_loss_reduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

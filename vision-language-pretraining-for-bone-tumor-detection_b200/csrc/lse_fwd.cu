@@ -44,6 +44,10 @@ struct LseParams {
   float* part_m;        // [n_chunks * 2][n_rows] raw (unscaled) running max of <X_i, Y_j>
   float* part_l;
   float* diag;          // [n_rows]: raw <X_i, Y_{i - diag_shift}>
+  // fused column statistics (kCols): per (row block, column) partial over the block's 128 rows,
+  // sum_i exp2(k c_ij - ref) with a log2-domain reference `ref`; the positive pair is left out
+  float* col_ref;       // [n_row_blocks][total_tiles * 128]
+  float* col_l;         // [n_row_blocks][total_tiles * 128]
 };
 
 struct FwdBarriers {
@@ -54,8 +58,15 @@ struct FwdBarriers {
   uint64_t x_ready;
   uint64_t x_free;
   uint32_t tmem_base;
+  uint32_t pad_;
+  float col_s[2][8][64];   // [tile parity][softmax warp][column of its half]: warp partial sums
+  float col_r[2][8];       // their log2-domain references
 };
 
+constexpr float COL_HEADROOM = 100.f;  // partial sums carry 2^100: 226 log2 units of range below a
+                                       // warp's largest row maximum before a term can underflow
+
+template <bool kCols>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -245,12 +256,66 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int j = 0; j < 64; j += 2) {
-            s0 += ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -m_new));
-            s1 += ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new));
+            const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -m_new));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new));
+            s0 += e0;
+            s1 += e1;
+            if (kCols) {
+              v[j] = __float_as_uint(e0);
+              v[j + 1] = __float_as_uint(e1);
+            }
           }
           l_run = l_run * ex2_approx(m_run - m_new) + (s0 + s1);
           m_run = m_new;
           mraw_run = mraw_new;
+        } else if (kCols) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = 0u;
+        }
+
+        if (kCols) {
+          // ---- column sums of this 32-row x 64-column slab: sum_i e_ij * 2^(m_i - R + 100) ----
+          float R = (row_ok && mraw_new != -INFINITY) ? m_new : -INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, o));
+          const float f = (row_ok && mraw_new != -INFINITY)
+                              ? ex2_approx(m_new - R + COL_HEADROOM) : 0.f;
+          float c[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) c[j] = __uint_as_float(v[j]) * f;
+          // butterfly: after the xor-16/8/4/2/1 steps lane L holds columns 2L and 2L+1
+#pragma unroll
+          for (int w = 32, o = 16; o > 0; w >>= 1, o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float send = up ? c[j] : c[j + w];
+              const float keep = up ? c[j + w] : c[j];
+              c[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          const uint32_t par = tile_ctr & 1, wslot = warp - 2;
+          *reinterpret_cast<float2*>(&bars->col_s[par][wslot][2 * lane]) = make_float2(c[0], c[1]);
+          if (lane == 0) bars->col_r[par][wslot] = R - COL_HEADROOM;
+          bar_sync(2, 256);
+          const uint32_t st = wslot * 32 + lane;   // 0..255; the first 128 threads own one column
+          if (st < 128) {
+            const uint32_t hh = st >> 6, cc = st & 63;   // warps of half hh: slots hh*4 .. hh*4+3
+            float r4[4], l4[4], M = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              r4[q] = bars->col_r[par][hh * 4 + q];
+              l4[q] = bars->col_s[par][hh * 4 + q][cc];
+              M = fmaxf(M, r4[q]);
+            }
+            float l = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (r4[q] != -INFINITY) l += l4[q] * ex2_approx(r4[q] - M);
+            const size_t o = (size_t)rb * ((size_t)p.total_tiles * 128) + (size_t)t * 128 + st;
+            p.col_ref[o] = M;
+            p.col_l[o] = l;
+          }
         }
       }
       if (row_ok) {
@@ -300,12 +365,36 @@ __global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* 
   }
   const float tot = l + t;
   const float lg = (t == 1.0f) ? log1pf(l) * kLog2e : log2f(tot);
+  // ln(sum_j exp(S_ij - S_ii)) = log1p(l * 2^gap): accurate for tiny losses even when `max` is only
+  // an upper reference (fused column statistics); falls back when 2^gap would overflow
+  const float loss2 = (diag && gap < 64.f) ? log1pf(l * exp2f(gap)) * kLog2e : lg + gap;
   if (out_max) out_max[i] = m;
   if (out_l) out_l[i] = l;
   if (out_lg2l) out_lg2l[i] = lg - fmaf(scale_log2, m, -m2);
   if (out_q) out_q[i] = l / tot;
-  if (out_loss) out_loss[i] = (lg + gap) * kLn2;
+  if (out_loss) out_loss[i] = loss2 * kLn2;
   if (lse) lse[i] = (m2 + lg) * kLn2;
+}
+
+// Fused forward: merge the per-row-block column partials (log2-domain reference, l) of one column
+// in fixed order and convert to the (raw max, l) convention of lse_merge_kernel.
+__global__ void col_merge_kernel(const float* __restrict__ col_ref, const float* __restrict__ col_l,
+                                 int n_row_blocks, size_t stride, int n_cols, float scale_log2,
+                                 float* __restrict__ out_max, float* __restrict__ out_l) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_cols) return;
+  float M = -INFINITY;
+  for (int r = 0; r < n_row_blocks; ++r) M = fmaxf(M, col_ref[(size_t)r * stride + j]);
+  float L = 0.f;
+  if (M != -INFINITY) {
+    for (int r = 0; r < n_row_blocks; ++r) {
+      const float rr = col_ref[(size_t)r * stride + j];
+      if (rr != -INFINITY) L += col_l[(size_t)r * stride + j] * exp2f(rr - M);
+    }
+  }
+  const float mx = M / scale_log2;                 // surrogate "max" in raw cosine units
+  out_max[j] = mx;
+  out_l[j] = (M != -INFINITY) ? L * exp2f(M - mx * scale_log2) : 0.f;   // relative to fl(k * mx)
 }
 
 // out2[0] = sum(row_loss), out2[1] = sum(col_loss); single block, fixed order => reproducible
@@ -371,6 +460,11 @@ static size_t lse_ws_bytes(int n_rows, int n_cols) {
   return (size_t)2 * (size_t)(max_chunks * 2) * (size_t)n_rows * sizeof(float);
 }
 
+static size_t lse_fused_ws_bytes(int n_rows, int n_cols) {
+  const size_t nrb = (n_rows + 127) / 128, nt = (n_cols + 127) / 128;
+  return lse_ws_bytes(n_rows, n_cols) + 2 * nrb * nt * 128 * sizeof(float);
+}
+
 }  // namespace vlp
 
 using namespace vlp;
@@ -400,12 +494,13 @@ size_t vlpclip_lse_workspace_bytes(int n_rows, int n_cols, int d) {
   return lse_ws_bytes(n_rows, n_cols);
 }
 
-int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols, int d,
-                    float scale, int diag_shift, float* row_max, float* row_l, float* diag,
-                    void* workspace, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,
+                        int d, float scale, int diag_shift, float* row_max, float* row_l, float* diag,
+                        float* col_max, float* col_l, void* workspace, size_t workspace_bytes,
+                        cudaStream_t stream) {
+  const bool fused = col_max != nullptr;
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "lse_fwd: empty problem (%d x %d)", n_rows, n_cols);
-  if (!x || !y || !row_max || !row_l || !diag || !workspace)
+  if (!x || !y || !row_max || !row_l || !diag || !workspace || (fused && !col_l))
     return fail(-1, "lse_fwd: null pointer");
   if (d <= 0 || d % 8 != 0 || d > 512)
     return fail(-1, "lse_fwd: embedding dim %d unsupported (need a multiple of 8, <= 512)", d);
@@ -416,9 +511,9 @@ int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, 
   if (!(scale > 0.f)) return fail(-1, "lse_fwd: scale must be positive");
   int rc = check_device_sm100();
   if (rc) return rc;
-  if (workspace_bytes < lse_ws_bytes(n_rows, n_cols))
-    return fail(-1, "lse_fwd: workspace too small (%zu < %zu)", workspace_bytes,
-                lse_ws_bytes(n_rows, n_cols));
+  const size_t need = fused ? lse_fused_ws_bytes(n_rows, n_cols) : lse_ws_bytes(n_rows, n_cols);
+  if (workspace_bytes < need)
+    return fail(-1, "lse_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
 
   LseParams p;
   p.x = (const __nv_bfloat16*)x;
@@ -438,6 +533,13 @@ int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, 
   p.part_m = (float*)workspace;
   p.part_l = p.part_m + (size_t)nparts * n_rows;
   p.diag = diag;
+  const size_t col_stride = (size_t)p.total_tiles * 128;
+  p.col_ref = nullptr;
+  p.col_l = nullptr;
+  if (fused) {
+    p.col_ref = (float*)((uint8_t*)workspace + lse_ws_bytes(n_rows, n_cols));
+    p.col_l = p.col_ref + (size_t)p.n_row_blocks * col_stride;
+  }
 
   CUtensorMap map_y;
   rc = make_tmap_sw128(&map_y, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
@@ -446,13 +548,18 @@ int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, 
   const size_t smem = FWD_STAGES * FWD_STAGE_BYTES + sizeof(FwdBarriers) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int n_items = p.n_row_blocks * p.n_chunks;
   const int grid = n_items < nsm ? n_items : nsm;
-  lse_partial_kernel<<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+  if (fused)
+    lse_partial_kernel<true><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+  else
+    lse_partial_kernel<false><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   lse_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_m, p.part_l, nullptr, nparts,
@@ -460,7 +567,35 @@ int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, 
                                                              row_l, nullptr, nullptr, nullptr);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
+  if (fused) {
+    col_merge_kernel<<<(n_cols + 127) / 128, 128, 0, stream>>>(
+        p.col_ref, p.col_l, p.n_row_blocks, col_stride, n_cols, p.scale_log2, col_max, col_l);
+    VLP_COUNT_LAUNCH(1);
+    VLP_CUDA_OK(cudaGetLastError());
+  }
   return 0;
+}
+
+int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols, int d,
+                    float scale, int diag_shift, float* row_max, float* row_l, float* diag,
+                    void* workspace, size_t workspace_bytes, void* stream_) {
+  return lse_fwd_impl(x, ldx, y, ldy, n_rows, n_cols, d, scale, diag_shift, row_max, row_l, diag,
+                      nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+size_t vlpclip_lse_fused_workspace_bytes(int n_rows, int n_cols, int d) {
+  (void)d;
+  if (n_rows <= 0 || n_cols <= 0) return 0;
+  return lse_fused_ws_bytes(n_rows, n_cols);
+}
+
+int vlpclip_lse_fwd_fused(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,
+                          int d, float scale, int diag_shift, float* row_max, float* row_l,
+                          float* diag, float* col_max, float* col_l, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
+  if (!col_max || !col_l) return fail(-1, "lse_fwd_fused: null column outputs");
+  return lse_fwd_impl(x, ldx, y, ldy, n_rows, n_cols, d, scale, diag_shift, row_max, row_l, diag,
+                      col_max, col_l, workspace, workspace_bytes, (cudaStream_t)stream_);
 }
 
 int vlpclip_lse_merge(const float* part_max, const float* part_l, const float* diag, int nparts,

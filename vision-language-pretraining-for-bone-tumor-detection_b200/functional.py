@@ -14,6 +14,7 @@ streams, autograd bookkeeping and (for the sharded variant) ``torch.distributed`
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -21,6 +22,9 @@ import torch
 from . import _lib, sharded
 
 LOGIT_SCALE_MAX = 100.0  # reference: torch.clamp(logit_scale.exp(), max=100)  (:457)
+# VLP_B200_EXACT_COLUMNS=1: give the column statistics their own sweep (exact column maxima)
+# instead of fusing them into the row sweep (see include/vlpclip.h: vlpclip_lse_fwd_fused)
+EXACT_COLUMNS = os.environ.get("VLP_B200_EXACT_COLUMNS", "0") == "1"
 
 
 # ----------------------------------------------------------------------------------------------
@@ -86,6 +90,36 @@ def lse_stats(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shi
                              diag.data_ptr(), ws.data_ptr(), nbytes, _stream())
     _lib.check(rc, "lse_fwd")
     return row_max, row_l, diag
+
+
+def lse_stats_fused(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shift: int = 0):
+    """One sweep over ``scale * x @ y.T``: row statistics (as ``lse_stats``) plus the statistics of
+    every column over the given rows: (row_max, row_l, diag, col_ref, col_l)."""
+    _require_cuda(x_bf16, "x")
+    _require_cuda(y_bf16, "y")
+    if x_bf16.dtype != torch.bfloat16 or y_bf16.dtype != torch.bfloat16:
+        raise ValueError("lse_stats_fused expects bf16 operands")
+    x = _as_2d_contig(x_bf16, "x")
+    y = _as_2d_contig(y_bf16, "y")
+    if x.shape[1] != y.shape[1]:
+        raise ValueError(f"embedding dims differ: {x.shape[1]} vs {y.shape[1]}")
+    n_rows, d = x.shape
+    n_cols = y.shape[0]
+    lib = _lib.load()
+    dev = x.device
+    row_max = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    row_l = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+    col_max = torch.empty(n_cols, dtype=torch.float32, device=dev)
+    col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
+    nbytes = lib.vlpclip_lse_fused_workspace_bytes(n_rows, n_cols, d)
+    ws = _ws(nbytes, dev)
+    rc = lib.vlpclip_lse_fwd_fused(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows,
+                                   n_cols, d, float(scale), int(diag_shift), row_max.data_ptr(),
+                                   row_l.data_ptr(), diag.data_ptr(), col_max.data_ptr(),
+                                   col_l.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    _lib.check(rc, "lse_fwd_fused")
+    return row_max, row_l, diag, col_max, col_l
 
 
 def merge_stats(part_max: torch.Tensor, part_l: torch.Tensor, diag: Optional[torch.Tensor],
@@ -154,6 +188,10 @@ class CudaOps:
         return lse_stats(x, y, scale, diag_shift)
 
     @staticmethod
+    def lse_stats_fused(x, y, scale, diag_shift):
+        return lse_stats_fused(x, y, scale, diag_shift)
+
+    @staticmethod
     def merge_stats(part_max, part_l, diag, scale):
         return merge_stats(part_max, part_l, diag, scale)[:4]
 
@@ -207,7 +245,8 @@ class _FusedClipLoss(torch.autograd.Function):
         if t_bf16 is None:
             t_bf16 = text_embeddings.detach().to(torch.bfloat16).contiguous()
 
-        plan = sharded.forward_plan(CudaOps, i_bf16, t_bf16, scale, group)
+        plan = sharded.forward_plan(CudaOps, i_bf16, t_bf16, scale, group,
+                                    exact_columns=EXACT_COLUMNS)
         world = plan["world"]
         ctx.group = group
         ctx.world, ctx.rank = world, plan["rank"]

@@ -13,6 +13,10 @@ backward  reduce_scatter(dT_all partial)          -> dT_loc           (N*D fp32 
           all_reduce(dscale)                                           (1 fp32)
 
 ``ops`` contract (shapes: x [n_rows, D], y [n_cols, D]):
+    lse_stats_fused(x, y, scale, diag_shift) -> (row_max, row_l, diag, col_ref, col_l)   [optional]
+        one sweep: the row statistics below plus, per column j of S, an upper reference
+        col_ref[j] >= max_i <x_i, y_j> and col_l[j] = sum over i != positive of
+        exp(scale*<x_i,y_j> - scale*col_ref[j]).
     lse_stats(x, y, scale, diag_shift) -> (row_max, row_l, diag)
         row_max[i] = max_j <x_i, y_j> (positive pair included), row_l[i] = sum over j != positive
         of exp(scale*<x_i,y_j> - scale*row_max[i]) (up to the fp32 rounding the merge undoes),
@@ -47,23 +51,35 @@ def all_gather_rows(t: torch.Tensor, group, world: int) -> torch.Tensor:
     return out
 
 
-def forward_plan(ops, i_loc, t_loc, scale: float, group=None):
-    """Returns a dict with the three losses (device scalars) and everything backward needs."""
+def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: bool = False):
+    """Returns a dict with the three losses (device scalars) and everything backward needs.
+
+    When ``ops`` offers ``lse_stats_fused`` (and ``exact_columns`` is False) the row and the column
+    statistics come out of ONE sweep over the logits; otherwise the columns get their own sweep."""
     world, rank = group_info(group)
     n_loc = i_loc.shape[0]
     n_glob = n_loc * world
     lo = rank * n_loc
     t_all = all_gather_rows(t_loc, group, world) if world > 1 else t_loc
 
-    # rows of S owned by the local images: complete after one sweep over T_all
-    r_max_p, r_l_p, r_diag = ops.lse_stats(i_loc, t_all, scale, -lo)
+    fused = (not exact_columns) and hasattr(ops, "lse_stats_fused")
+    if fused:
+        # one sweep: rows of S owned by the local images (complete) + partial column statistics
+        r_max_p, r_l_p, r_diag, c_max_p, c_l_p = ops.lse_stats_fused(i_loc, t_all, scale, -lo)
+        c_diag_own = r_diag                     # S_jj seen from column j is the same logit
+    else:
+        # rows of S owned by the local images: complete after one sweep over T_all
+        r_max_p, r_l_p, r_diag = ops.lse_stats(i_loc, t_all, scale, -lo)
+        # columns (= rows of S^T owned by the texts): partial over the local images
+        c_max_p, c_l_p, c_diag_full = ops.lse_stats(t_all, i_loc, scale, lo)
+        c_diag_own = c_diag_full[lo:lo + n_loc]
     r_max, r_lg, r_q, r_loss = ops.merge_stats(r_max_p, r_l_p, r_diag, scale)
-    # columns (= rows of S^T owned by the texts): partial over the local images
-    c_max_p, c_l_p, c_diag = ops.lse_stats(t_all, i_loc, scale, lo)
     if world > 1:
         c_max_p = all_gather_rows(c_max_p.unsqueeze(0), group, world)
         c_l_p = all_gather_rows(c_l_p.unsqueeze(0), group, world)
-        c_diag = all_gather_rows(c_diag[lo:lo + n_loc], group, world)
+        c_diag = all_gather_rows(c_diag_own, group, world)
+    else:
+        c_diag = c_diag_own
     c_max, c_lg, c_q, c_loss = ops.merge_stats(c_max_p, c_l_p, c_diag, scale)
     sums = ops.loss_sums(r_loss, c_loss[lo:lo + n_loc])
     if world > 1:
