@@ -22,10 +22,11 @@ for n in sizes:
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
     t_f = timeit(lambda: VF.lse_stats(I, T, s, 0))
+    t_ff = timeit(lambda: VF.lse_stats_fused(I, T, s, 0))
     rm, rl, rd = VF.lse_stats(I, T, s, 0); cm, cl, cd = VF.lse_stats(T, I, s, 0)
     rs = VF.merge_stats(rm, rl, rd, s)[:3]; cs = VF.merge_stats(cm, cl, cd, s)[:3]
     i16 = VF.cast_bf16_to_f16(I); t16 = VF.cast_bf16_to_f16(T)
     t_g = timeit(lambda: VF._grad(i16, t16, rs, cs, s, 0, n, 1.0, 1.0, True))
     fl = 2.0 * n * n * d
-    print(f"N={n} D={d}: lse_fwd {t_f:.3f} ms ({fl/t_f/1e9:.0f} TF/s)  grad {t_g:.3f} ms (alg {fl/t_g/1e9:.0f} / exec {2*fl/t_g/1e9:.0f} TF/s)"
-          f"  => step est {2*t_f+2*t_g:.3f} ms = {6*n*n*d/(2*t_f+2*t_g)/1e9/1645.6*100:.1f}% of peak")
+    print(f"N={n} D={d}: fused_fwd {t_ff:.3f} ms ({fl/t_ff/1e9:.0f} TF/s) lse_fwd {t_f:.3f} ms ({fl/t_f/1e9:.0f} TF/s)  grad {t_g:.3f} ms (alg {fl/t_g/1e9:.0f} / exec {2*fl/t_g/1e9:.0f} TF/s)"
+          f"  => step est {t_ff+2*t_g:.3f} ms = {6*n*n*d/(t_ff+2*t_g)/1e9/1645.6*100:.1f}% of peak")

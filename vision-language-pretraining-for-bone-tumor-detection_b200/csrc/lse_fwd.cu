@@ -25,7 +25,10 @@ constexpr int FWD_KB_PER_STAGE = 2;          // k-blocks (128 rows x 64 bf16 = 1
 constexpr int FWD_BOX_BYTES = 128 * 128;
 constexpr int FWD_STAGE_BYTES = FWD_KB_PER_STAGE * FWD_BOX_BYTES;
 constexpr int FWD_STAGES = 6;
-constexpr int FWD_THREADS = 320;
+constexpr int FWD_SMW = 16;                  // softmax warps: 4 TMEM lane quarters x 4 column groups
+constexpr int FWD_CG = FWD_SMW / 4;          // column groups per tile
+constexpr int FWD_CPT = 128 / FWD_CG;        // columns per thread (32)
+constexpr int FWD_THREADS = 64 + FWD_SMW * 32;
 constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: up to 256 columns (d <= 512)
 constexpr uint32_t TMEM_S_COL = 256;    // two S buffers of 128 columns
 
@@ -41,7 +44,7 @@ struct LseParams {
   int diag_shift;       // delta_ij = 1 iff i == j + diag_shift
   float scale;          // s
   float scale_log2;     // s * log2(e)
-  float* part_m;        // [n_chunks * 2][n_rows] raw (unscaled) running max of <X_i, Y_j>
+  float* part_m;        // [n_chunks * FWD_CG][n_rows] raw (unscaled) running max of <X_i, Y_j>
   float* part_l;
   float* diag;          // [n_rows]: raw <X_i, Y_{i - diag_shift}>
   // fused column statistics (kCols): per (row block, column) partial over the block's 128 rows,
@@ -59,8 +62,8 @@ struct FwdBarriers {
   uint64_t x_free;
   uint32_t tmem_base;
   uint32_t pad_;
-  float col_s[2][8][64];   // [tile parity][softmax warp][column of its half]: warp partial sums
-  float col_r[2][8];       // their log2-domain references
+  float col_s[2][FWD_SMW][FWD_CPT];   // [tile parity][softmax warp][its column]: warp partial sums
+  float col_r[2][FWD_SMW];            // their log2-domain references
 };
 
 constexpr float COL_HEADROOM = 100.f;  // partial sums carry 2^100: 226 log2 units of range below a
@@ -84,9 +87,9 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->s_empty[i]), 8);  // one arrive per softmax warp
+      mbar_init(smem_u32(&bars->s_empty[i]), FWD_SMW);  // one arrive per softmax warp
     }
-    mbar_init(smem_u32(&bars->x_ready), 8);
+    mbar_init(smem_u32(&bars->x_ready), FWD_SMW);
     mbar_init(smem_u32(&bars->x_free), 1);
     fence_mbar_init();
   }
@@ -166,8 +169,10 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
   } else {
     // ================= softmax warps =================
-    const uint32_t quarter = warp & 3;           // TMEM lane quarter this warp may touch
-    const uint32_t half = (warp - 2) >> 2;       // which 64-column half of the tile
+    // thread = (row, column group): quarter = TMEM lane quarter of the warp, cg = 32-column group
+    const uint32_t quarter = warp & 3;
+    const uint32_t wslot = warp - 2;             // 0 .. FWD_SMW-1
+    const uint32_t cg = wslot >> 2;
     const uint32_t row_in_blk = quarter * 32 + lane;
     const uint32_t lane_addr = (quarter * 32u) << 16;
     const int dp = p.kblocks * 64;               // padded K
@@ -186,12 +191,12 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         tc_fence_after();
       }
       {
-        const int k_begin = half * (dp / 2);
+        const int k_begin = cg * (dp / FWD_CG);    // this thread's share of the row: dp/4 elements
         const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)(row_ok ? row : 0) * p.ldx);
-        for (int c0 = 0; c0 < dp / 4; c0 += 16) {
-          uint32_t v[16];
+        for (int c0 = 0; c0 < dp / (2 * FWD_CG); c0 += 8) {
+          uint32_t v[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 2; ++q) {
             const int k = k_begin + c0 * 2 + q * 8;
             uint4 w = make_uint4(0, 0, 0, 0);
             if (row_ok && k < p.d) w = __ldg(src + (k >> 3));
@@ -200,7 +205,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
             v[q * 4 + 2] = w.z;
             v[q * 4 + 3] = w.w;
           }
-          tmem_st_x16(tmem + lane_addr + TMEM_X_COL + k_begin / 2 + c0, v);
+          tmem_st_x8(tmem + lane_addr + TMEM_X_COL + k_begin / 2 + c0, v);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -215,47 +220,41 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         const uint32_t buf = tile_ctr & 1;
         mbar_wait(smem_u32(&bars->s_full[buf]), (tile_ctr >> 1) & 1);
         tc_fence_after();
-        uint32_t v[64];
-        {
-          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-          uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-          const uint32_t a = tmem + lane_addr + TMEM_S_COL + buf * 128 + half * 64;
-          tmem_ld_x32(a, v0);
-          tmem_ld_x32(a + 32, v1);
-          tmem_ld_wait();
-        }
+        uint32_t v[FWD_CPT];
+        tmem_ld_x32(tmem + lane_addr + TMEM_S_COL + buf * 128 + cg * FWD_CPT, v);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
 
-        const int col0 = t * 128 + half * 64;
+        const int col0 = t * 128 + cg * FWD_CPT;
         // columns past n_cols were zero-filled by TMA: mask them out of the statistics
-        if (col0 + 64 > p.n_cols) {
+        if (col0 + FWD_CPT > p.n_cols) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
+          for (int j = 0; j < FWD_CPT; ++j)
             if (col0 + j >= p.n_cols) v[j] = __float_as_uint(-INFINITY);
         }
         float mx = __uint_as_float(v[0]);
 #pragma unroll
-        for (int j = 1; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 1; j < FWD_CPT; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
         // positive pair: remember its raw logit, keep it in the running max, but leave it out of
         // the sum (the merge step adds it back through log1p -> no cancellation for tiny losses)
-        if (__any_sync(0xffffffffu, dcol >= col0 && dcol < col0 + 64)) {
+        if (__any_sync(0xffffffffu, dcol >= col0 && dcol < col0 + FWD_CPT)) {
           float dv = 0.f;
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
+          for (int j = 0; j < FWD_CPT; ++j)
             if (col0 + j == dcol) {
               dv = __uint_as_float(v[j]);
               v[j] = __float_as_uint(-INFINITY);
             }
-          if (row_ok && dcol >= col0 && dcol < col0 + 64) p.diag[row] = dv;
+          if (row_ok && dcol >= col0 && dcol < col0 + FWD_CPT) p.diag[row] = dv;
         }
         const float mraw_new = fmaxf(mraw_run, mx);
         const float m_new = mraw_new * p.scale_log2;  // log2-domain reference of this row
         if (mraw_new != -INFINITY) {
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 64; j += 2) {
+          for (int j = 0; j < FWD_CPT; j += 2) {
             const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -m_new));
             const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new));
             s0 += e0;
@@ -270,22 +269,22 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           mraw_run = mraw_new;
         } else if (kCols) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = 0u;
+          for (int j = 0; j < FWD_CPT; ++j) v[j] = 0u;
         }
 
         if (kCols) {
-          // ---- column sums of this 32-row x 64-column slab: sum_i e_ij * 2^(m_i - R + 100) ----
+          // ---- column sums of this 32-row x 32-column slab: sum_i e_ij * 2^(m_i - R + 100) ----
           float R = (row_ok && mraw_new != -INFINITY) ? m_new : -INFINITY;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) R = fmaxf(R, __shfl_xor_sync(0xffffffffu, R, o));
           const float f = (row_ok && mraw_new != -INFINITY)
                               ? ex2_approx(m_new - R + COL_HEADROOM) : 0.f;
-          float c[64];
+          float c[FWD_CPT];
 #pragma unroll
-          for (int j = 0; j < 64; ++j) c[j] = __uint_as_float(v[j]) * f;
-          // butterfly: after the xor-16/8/4/2/1 steps lane L holds columns 2L and 2L+1
+          for (int j = 0; j < FWD_CPT; ++j) c[j] = __uint_as_float(v[j]) * f;
+          // butterfly: after the xor-16/8/4/2/1 steps lane L holds column L of the group
 #pragma unroll
-          for (int w = 32, o = 16; o > 0; w >>= 1, o >>= 1) {
+          for (int w = FWD_CPT / 2, o = 16; o > 0; w >>= 1, o >>= 1) {
             const bool up = (lane & o) != 0;
 #pragma unroll
             for (int j = 0; j < w; ++j) {
@@ -294,18 +293,18 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
               c[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
           }
-          const uint32_t par = tile_ctr & 1, wslot = warp - 2;
-          *reinterpret_cast<float2*>(&bars->col_s[par][wslot][2 * lane]) = make_float2(c[0], c[1]);
+          const uint32_t par = tile_ctr & 1;
+          bars->col_s[par][wslot][lane] = c[0];
           if (lane == 0) bars->col_r[par][wslot] = R - COL_HEADROOM;
-          bar_sync(2, 256);
-          const uint32_t st = wslot * 32 + lane;   // 0..255; the first 128 threads own one column
+          bar_sync(2, FWD_SMW * 32);
+          const uint32_t st = wslot * 32 + lane;   // the first 128 softmax threads own one column
           if (st < 128) {
-            const uint32_t hh = st >> 6, cc = st & 63;   // warps of half hh: slots hh*4 .. hh*4+3
+            const uint32_t g = st >> 5, cc = st & 31;   // warps of column group g: slots g*4 .. g*4+3
             float r4[4], l4[4], M = -INFINITY;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              r4[q] = bars->col_r[par][hh * 4 + q];
-              l4[q] = bars->col_s[par][hh * 4 + q][cc];
+              r4[q] = bars->col_r[par][g * 4 + q];
+              l4[q] = bars->col_s[par][g * 4 + q][cc];
               M = fmaxf(M, r4[q]);
             }
             float l = 0.f;
@@ -319,7 +318,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         }
       }
       if (row_ok) {
-        const size_t o = (size_t)(chunk * 2 + half) * p.n_rows + row;
+        const size_t o = (size_t)(chunk * FWD_CG + cg) * p.n_rows + row;
         p.part_m[o] = mraw_run;
         p.part_l[o] = l_run;
       }
@@ -457,7 +456,7 @@ static void pick_chunks(int n_row_blocks, int total_tiles, int n_sm, int* n_chun
 static size_t lse_ws_bytes(int n_rows, int n_cols) {
   const int total_tiles = (n_cols + 127) / 128;
   const int max_chunks = total_tiles < 64 ? total_tiles : 64;
-  return (size_t)2 * (size_t)(max_chunks * 2) * (size_t)n_rows * sizeof(float);
+  return (size_t)2 * (size_t)(max_chunks * FWD_CG) * (size_t)n_rows * sizeof(float);
 }
 
 static size_t lse_fused_ws_bytes(int n_rows, int n_cols) {
@@ -529,7 +528,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   p.diag_shift = diag_shift;
   p.scale = scale;
   p.scale_log2 = scale * kLog2e;
-  const int nparts = p.n_chunks * 2;
+  const int nparts = p.n_chunks * FWD_CG;
   p.part_m = (float*)workspace;
   p.part_l = p.part_m + (size_t)nparts * n_rows;
   p.diag = diag;
