@@ -96,7 +96,9 @@ int vlpclip_loss_reduce(const float* row_loss, const float* col_loss, int n, flo
  * X, Y: fp16 copies of the embeddings ([n_rows, d] / [n_cols, d], row strides ldx / ldy).
  * (x_max, x_lg2l, x_q)[n_rows], (y_max, y_lg2l, y_q)[n_cols]: merged statistics
  * (vlpclip_lse_merge) of the rows of S owned by X / by Y.  delta_ij = 1 iff i == j + diag_shift.
- * dX: [n_rows, d] fp32 (row stride d), overwritten.
+ * dX: [n_rows, d] (row stride d), overwritten; fp32, or bf16 when dx_bf16 != 0.
+ * out_mul (optional device scalar, may be NULL): multiplied into dX (the upstream gradient of
+ * loss.backward(); dscale is NOT multiplied).
  * dscale (optional, may be NULL): receives sum_ij G_ij <X_i, Y_j> (fp32, one value).
  * Replaces autograd of VisionLanguageModule.py:459, :550-552.
  */
@@ -104,8 +106,8 @@ size_t vlpclip_grad_workspace_bytes(int n_rows, int n_cols, int d);
 int vlpclip_grad(const void* x_f16, int ldx, const void* y_f16, int ldy, const float* x_max,
                  const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
                  const float* y_q, int n_rows, int n_cols, int d, float scale, int diag_shift,
-                 int n_global, float w_row, float w_col, float* dx, float* dscale, void* workspace,
-                 size_t workspace_bytes, void* stream);
+                 int n_global, float w_row, float w_col, const float* out_mul, int dx_bf16, void* dx,
+                 float* dscale, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- prologue: emb = normalize(feat @ W) (VisionLanguageModule.py:448-453) ----
  * feat [n, f] fp32, W [f, d] fp32 (x @ W convention, not nn.Linear).

@@ -53,7 +53,8 @@ class ContractOps:
         return torch.stack([row_loss.sum(), col_loss.sum()])
 
     @staticmethod
-    def grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale):
+    def grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
+             out_mul=None, out_dtype=None):
         x = x.double(); y = y.double()
         xm, xlg, xq = x_stats
         ym, ylg, yq = y_stats
@@ -69,6 +70,8 @@ class ContractOps:
         g[rows[has], dcol[has]] = -(w_row * xq[rows[has]] + w_col * yq[dcol[has]])
         g = g / (2.0 * n_global)
         dx = scale * (g @ y)
+        if out_mul is not None:
+            dx = dx * out_mul
         ds = (g * c).sum().reshape(1) if want_dscale else None
         return dx, ds
 

@@ -32,8 +32,8 @@ _SIGNATURES = {
     "vlpclip_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlpclip_grad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
-                             c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
-                             c_void_p]),
+                             c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                             c_size_t, c_void_p]),
     "vlpclip_project_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlpclip_project_normalize_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

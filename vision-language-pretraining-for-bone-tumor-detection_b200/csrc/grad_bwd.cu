@@ -18,6 +18,7 @@
 //                       tcgen05.commit. Epilogue scales and stores (or red.adds when the column
 //                       range is split across clusters).
 // Neither S nor G ever leaves the SM pair.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/vlpclip.h"
@@ -56,7 +57,10 @@ struct GradParams {
   int diag_shift;
   float scale_log2;
   float out_scale;      // scale / (2 n_global) / 2^13
-  float* dx;            // [n_rows, d] (n_chunks == 1) or per-chunk partials [n_chunks][n_rows, d]
+  void* dx;             // [n_rows, d] final output (n_chunks == 1; fp32 or bf16) or fp32 per-chunk
+                        // partials [n_chunks][n_rows, d]
+  int dx_bf16;          // final output dtype when written by this kernel
+  const float* out_mul; // optional device scalar multiplied into the output (upstream gradient)
   size_t chunk_stride;  // elements between the partial buffers of consecutive chunks
   float* ds_part;       // [n_items * 8] or nullptr
 };
@@ -466,22 +470,44 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         mbar_wait(smem_u32(&bars->acc_full), item_ctr & 1);
         tc_fence_after();
         const int chunk = item / p.n_row_blocks;
-        float* orow = p.dx + (size_t)chunk * p.chunk_stride + (size_t)(row < p.n_rows ? row : 0) * p.d;
+        const bool final_out = p.n_chunks == 1;
+        const float mulv = (final_out && p.out_mul) ? p.out_scale * __ldg(p.out_mul) : p.out_scale;
+        const size_t roff = (size_t)chunk * p.chunk_stride + (size_t)(row < p.n_rows ? row : 0) * p.d;
+        float* orow = reinterpret_cast<float*>(p.dx) + roff;
+        __nv_bfloat16* orow_b = reinterpret_cast<__nv_bfloat16*>(p.dx) + roff;
         for (int c = 0; c < p.kblocks * 64; c += 32) {
           uint32_t v[32];
           tmem_ld_x32(tmem + lane_addr + c, v);
           tmem_ld_wait();
           if (row < p.n_rows) {
+            if (final_out && p.dx_bf16) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (c + j < p.d) {
-                float4 o;
-                o.x = __uint_as_float(v[j + 0]) * p.out_scale;
-                o.y = __uint_as_float(v[j + 1]) * p.out_scale;
-                o.z = __uint_as_float(v[j + 2]) * p.out_scale;
-                o.w = __uint_as_float(v[j + 3]) * p.out_scale;
-                *reinterpret_cast<float4*>(orow + c + j) = o;
-              }
+              for (int j = 0; j < 32; j += 8)
+                if (c + j < p.d) {
+                  uint4 o;
+                  __nv_bfloat162 b;
+                  b = __floats2bfloat162_rn(__uint_as_float(v[j + 0]) * mulv, __uint_as_float(v[j + 1]) * mulv);
+                  o.x = *reinterpret_cast<uint32_t*>(&b);
+                  b = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) * mulv, __uint_as_float(v[j + 3]) * mulv);
+                  o.y = *reinterpret_cast<uint32_t*>(&b);
+                  b = __floats2bfloat162_rn(__uint_as_float(v[j + 4]) * mulv, __uint_as_float(v[j + 5]) * mulv);
+                  o.z = *reinterpret_cast<uint32_t*>(&b);
+                  b = __floats2bfloat162_rn(__uint_as_float(v[j + 6]) * mulv, __uint_as_float(v[j + 7]) * mulv);
+                  o.w = *reinterpret_cast<uint32_t*>(&b);
+                  *reinterpret_cast<uint4*>(orow_b + c + j) = o;
+                }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (c + j < p.d) {
+                  float4 o;
+                  o.x = __uint_as_float(v[j + 0]) * mulv;
+                  o.y = __uint_as_float(v[j + 1]) * mulv;
+                  o.z = __uint_as_float(v[j + 2]) * mulv;
+                  o.w = __uint_as_float(v[j + 3]) * mulv;
+                  *reinterpret_cast<float4*>(orow + c + j) = o;
+                }
+            }
           }
         }
         tc_fence_before();
@@ -497,16 +523,16 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
 }
 
-// Global range of the log2-domain LSEs (rows of X and of Y, direction weights folded in):
-// out[0] = C (midpoint), flag = 1 when the spread allows the single-ex2 path.
+// Global range of the log2-domain LSEs (rows of X and of Y, direction weights folded in), stage 1:
+// RANGE_BLOCKS blocks each write their (min, max) to part[2 * block].
+constexpr int RANGE_BLOCKS = 32;
 __global__ void lse_range_kernel(const float* __restrict__ xmax, const float* __restrict__ xlg,
                                  int nx, float log2wx, const float* __restrict__ ymax,
                                  const float* __restrict__ ylg, int ny, float log2wy,
-                                 float scale_log2, int force_slow, float* __restrict__ c_out,
-                                 int* __restrict__ flag) {
-  __shared__ float smin[1024], smax[1024];
+                                 float scale_log2, float* __restrict__ part) {
+  __shared__ float smin[256], smax[256];
   float lo = INFINITY, hi = -INFINITY;
-  for (int i = threadIdx.x; i < nx + ny; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx + ny; i += gridDim.x * blockDim.x) {
     const float e = i < nx ? fmaf(scale_log2, xmax[i], xlg[i] - log2wx)
                            : fmaf(scale_log2, ymax[i - nx], ylg[i - nx] - log2wy);
     if (e == e && fabsf(e) != INFINITY) {   // a zero direction weight gives +inf: ignore
@@ -525,12 +551,23 @@ __global__ void lse_range_kernel(const float* __restrict__ xmax, const float* __
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float l = smin[0], h = smax[0];
-    // (a zero direction weight makes one factor of the factorisation vanish: use two ex2)
-    const bool ok = !force_slow && (h >= l) && (h - l) < 60.f;
-    c_out[0] = ok ? 0.5f * (l + h) : 0.f;
-    flag[0] = ok ? 1 : 0;
+    part[2 * blockIdx.x] = smin[0];
+    part[2 * blockIdx.x + 1] = smax[0];
   }
+}
+
+// stage 2 (inlined into the consumers of the range): midpoint C and the single-ex2 flag
+__device__ __forceinline__ void lse_range_finish(const float* __restrict__ part, int force_slow,
+                                                 float& c_mid, int& fast) {
+  float l = INFINITY, h = -INFINITY;
+  for (int b = 0; b < RANGE_BLOCKS; ++b) {
+    l = fminf(l, part[2 * b]);
+    h = fmaxf(h, part[2 * b + 1]);
+  }
+  // (a zero direction weight makes one factor of the factorisation vanish: use two ex2)
+  const bool ok = !force_slow && (h >= l) && (h - l) < 60.f;
+  c_mid = ok ? 0.5f * (l + h) : 0.f;
+  fast = ok ? 1 : 0;
 }
 
 // pad the per-row statistics to whole tiles: max -> 0, lg2l -> +inf (probability 0); a direction
@@ -538,8 +575,19 @@ __global__ void lse_range_kernel(const float* __restrict__ xmax, const float* __
 // with e = k*max + lg2l is the fast-path row (sign +1) / column (sign -1) factor, 0 when padded.
 __global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __restrict__ lg, int n,
                                  int n_pad, float log2w, float scale_log2, float sign,
-                                 const float* __restrict__ c_ptr, float* __restrict__ mx_out,
+                                 const float* __restrict__ range_part, int force_slow,
+                                 int* __restrict__ fast_flag, float* __restrict__ mx_out,
                                  float* __restrict__ lg_out, float* __restrict__ fac_out) {
+  __shared__ float c_sh;
+  if (threadIdx.x == 0) {
+    float c;
+    int fast;
+    lse_range_finish(range_part, force_slow, c, fast);
+    c_sh = c;
+    if (blockIdx.x == 0) *fast_flag = fast;
+  }
+  __syncthreads();
+  const float c_mid = c_sh;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) {
     const float m = i < n ? mx[i] : 0.f;
@@ -547,15 +595,17 @@ __global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __re
     mx_out[i] = m;
     lg_out[i] = l;
     const float e = fmaf(scale_log2, m, l);
-    fac_out[i] = (i < n && fabsf(e) != INFINITY) ? exp2f(sign * (e - c_ptr[0])) : 0.f;
+    fac_out[i] = (i < n && fabsf(e) != INFINITY) ? exp2f(sign * (e - c_mid)) : 0.f;
   }
 }
 
-// dx = sum over chunks of the per-chunk partial blocks, fixed order (bit reproducible)
+// dx = mul * sum over chunks of the per-chunk partial blocks, fixed order (bit reproducible)
 __global__ void dx_reduce_kernel(const float4* __restrict__ part, size_t chunk_stride4, int n_chunks,
-                                 size_t n4, float4* __restrict__ dx) {
+                                 size_t n4, const float* __restrict__ out_mul, int out_bf16,
+                                 void* __restrict__ dx) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float m = out_mul ? __ldg(out_mul) : 1.f;
   for (; i < n4; i += stride) {
     float4 a = part[i];
     for (int c = 1; c < n_chunks; ++c) {
@@ -565,7 +615,16 @@ __global__ void dx_reduce_kernel(const float4* __restrict__ part, size_t chunk_s
       a.z += b.z;
       a.w += b.w;
     }
-    dx[i] = a;
+    if (out_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x * m, a.y * m);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(a.z * m, a.w * m);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(dx)[i] = o;
+    } else {
+      reinterpret_cast<float4*>(dx)[i] = make_float4(a.x * m, a.y * m, a.z * m, a.w * m);
+    }
   }
 }
 
@@ -618,7 +677,7 @@ static size_t grad_ws_bytes(int n_rows, int n_cols, int d) {
   pick_chunks_pairs((int)nrb, (int)nt, n_pairs_of_device(), &n_chunks, &tpc);
   const size_t partials = n_chunks > 1 ? align256((size_t)n_chunks * n_rows * d * 4) : 0;
   return 3 * align256(nrb * 128 * 4) + 3 * align256(nt * 128 * 4) + align256(nrb * 16 * 8 * 4) +
-         partials + 512;
+         partials + 1024;
 }
 
 }  // namespace vlp
@@ -636,8 +695,8 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
                  const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
                  const float* y_q, int n_rows,
                  int n_cols, int d, float scale, int diag_shift, int n_global, float w_row,
-                 float w_col, float* dx, float* dscale, void* workspace, size_t workspace_bytes,
-                 void* stream_) {
+                 float w_col, const float* out_mul, int dx_bf16, void* dx, float* dscale,
+                 void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "grad: empty problem (%d x %d)", n_rows, n_cols);
   if (!x || !y || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q || !dx || !workspace)
@@ -689,13 +748,15 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   ws += align256((size_t)npx * 4);
   float* yc = (float*)ws;
   ws += align256((size_t)npy * 4);
-  float* c_mid = (float*)ws;
-  int* fast_flag = (int*)(ws + 128);
-  ws += 256;
+  float* range_part = (float*)ws;                 // RANGE_BLOCKS (min, max) pairs
+  int* fast_flag = (int*)(ws + 256);
+  ws += 512;
   float* ds_part = (float*)ws;
   ws += align256((size_t)p.n_row_blocks * 16 * 8 * 4);
   float* dx_part = (float*)ws;
-  p.dx = p.n_chunks > 1 ? dx_part : dx;
+  p.dx = p.n_chunks > 1 ? (void*)dx_part : dx;
+  p.dx_bf16 = dx_bf16;
+  p.out_mul = out_mul;
   p.chunk_stride = (size_t)n_rows * d;
   p.xmax = xmax;
   p.xlg = xlg;
@@ -706,15 +767,17 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   p.fast_flag = fast_flag;
   p.ds_part = dscale ? ds_part : nullptr;
   const float l2wr = log2f(w_row), l2wc = log2f(w_col);
-  lse_range_kernel<<<1, 1024, 0, stream>>>(x_max, x_lg2l, n_rows, l2wr, y_max, y_lg2l, n_cols, l2wc,
-                                           p.scale_log2, (w_row == 0.f || w_col == 0.f) ? 1 : 0, c_mid,
-                                           fast_flag);
+  const int force_slow = (w_row == 0.f || w_col == 0.f) ? 1 : 0;
+  lse_range_kernel<<<RANGE_BLOCKS, 256, 0, stream>>>(x_max, x_lg2l, n_rows, l2wr, y_max, y_lg2l,
+                                                     n_cols, l2wc, p.scale_log2, range_part);
   VLP_COUNT_LAUNCH(1);
   stats_pad_kernel<<<(npx + 255) / 256, 256, 0, stream>>>(x_max, x_lg2l, n_rows, npx, l2wr,
-                                                          p.scale_log2, 1.f, c_mid, xmax, xlg, xr);
+                                                          p.scale_log2, 1.f, range_part, force_slow,
+                                                          fast_flag, xmax, xlg, xr);
   VLP_COUNT_LAUNCH(1);
   stats_pad_kernel<<<(npy + 255) / 256, 256, 0, stream>>>(y_max, y_lg2l, n_cols, npy, l2wc,
-                                                          p.scale_log2, -1.f, c_mid, ymax, ylg, yc);
+                                                          p.scale_log2, -1.f, range_part, force_slow,
+                                                          fast_flag, ymax, ylg, yc);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
 
@@ -740,8 +803,8 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
     const size_t n4 = (size_t)n_rows * d / 4;
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    dx_reduce_kernel<<<blocks, 256, 0, stream>>>((const float4*)dx_part, n4, p.n_chunks, n4,
-                                                 (float4*)dx);
+    dx_reduce_kernel<<<blocks, 256, 0, stream>>>((const float4*)dx_part, n4, p.n_chunks, n4, out_mul,
+                                                 dx_bf16, dx);
     VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
   }

@@ -160,13 +160,18 @@ def _loss_sums(row_loss: torch.Tensor, col_loss: torch.Tensor) -> torch.Tensor:
 
 
 def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_global: int,
-          w_row: float = 1.0, w_col: float = 1.0, want_dscale: bool = False):
-    """x_stats / y_stats = (max, lg2l, q) of the rows of S owned by X / Y."""
+          w_row: float = 1.0, w_col: float = 1.0, want_dscale: bool = False,
+          out_mul: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32):
+    """x_stats / y_stats = (max, lg2l, q) of the rows of S owned by X / Y.
+
+    ``out_mul`` (fp32 device scalar) is folded into dX by the kernel epilogue; ``out_dtype`` may be
+    float32 or bfloat16."""
     lib = _lib.load()
     n_rows, d = x_f16.shape
     n_cols = y_f16.shape[0]
     dev = x_f16.device
-    dx = torch.empty(n_rows, d, dtype=torch.float32, device=dev)
+    assert out_dtype in (torch.float32, torch.bfloat16)
+    dx = torch.empty(n_rows, d, dtype=out_dtype, device=dev)
     ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
     nbytes = lib.vlpclip_grad_workspace_bytes(n_rows, n_cols, d)
     ws = _ws(nbytes, dev)
@@ -174,7 +179,9 @@ def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_globa
                           x_stats[0].data_ptr(), x_stats[1].data_ptr(), x_stats[2].data_ptr(),
                           y_stats[0].data_ptr(), y_stats[1].data_ptr(), y_stats[2].data_ptr(),
                           n_rows, n_cols, d, float(scale), int(diag_shift), int(n_global),
-                          float(w_row), float(w_col), dx.data_ptr(),
+                          float(w_row), float(w_col),
+                          out_mul.data_ptr() if out_mul is not None else None,
+                          1 if out_dtype == torch.bfloat16 else 0, dx.data_ptr(),
                           ds.data_ptr() if want_dscale else None, ws.data_ptr(), nbytes, _stream())
     _lib.check(rc, "grad")
     return dx, ds
@@ -200,8 +207,10 @@ class CudaOps:
         return _loss_sums(row_loss, col_loss)
 
     @staticmethod
-    def grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale):
-        return _grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale)
+    def grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
+             out_mul=None, out_dtype=torch.float32):
+        return _grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
+                     out_mul, out_dtype)
 
     @staticmethod
     def to_backward_operand(x_bf16):
@@ -290,20 +299,21 @@ class _FusedClipLoss(torch.autograd.Function):
         t_all_f16 = t_f16 if t_f16 is not None else CudaOps.to_backward_operand(t_all_bf16)
         world = ctx.world
         gs = ctx.grad_scale
+        mul = (mul.detach().float().reshape(1) * gs).contiguous()   # device scalar, no host sync
+        kdt = lambda dt: dt if dt in (torch.float32, torch.bfloat16) else torch.float32  # noqa: E731
         d_i, d_t, ds = sharded.backward_plan(
             CudaOps, i_f16, t_all_f16, r_stats, c_stats, ctx.scale, ctx.n_loc, ctx.n_glob, ctx.rank,
-            world, ctx.group, w_r, w_c, need_i, need_t, need_ls)
+            world, ctx.group, w_r, w_c, need_i, need_t, need_ls, out_mul=mul,
+            out_dtypes=(kdt(ctx.in_dtypes[0]), kdt(ctx.in_dtypes[1])))
         d_ls = None
         if need_ls:
             # d/dl clamp(e^l, max=100) = e^l if e^l <= 100 else 0   (reference :456-457)
             d_ls = ds * (0.0 if ctx.clamped else ctx.exp_ls)
-            d_ls = (d_ls * mul * gs).to(ctx.in_dtypes[2]).reshape(ctx.ls_shape)
-        if need_i:
-            d_i = (d_i * (mul * gs)).to(ctx.in_dtypes[0])
-        else:
-            d_i = None
-        if need_t:
-            d_t = (d_t * (mul * gs)).to(ctx.in_dtypes[1])
+            d_ls = (d_ls * mul).to(ctx.in_dtypes[2]).reshape(ctx.ls_shape)
+        if need_i and d_i.dtype != ctx.in_dtypes[0]:
+            d_i = d_i.to(ctx.in_dtypes[0])
+        if need_t and d_t.dtype != ctx.in_dtypes[1]:
+            d_t = d_t.to(ctx.in_dtypes[1])
         return d_i, d_t, d_ls, None, None, None, None, None, None
 
 

@@ -93,26 +93,33 @@ def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: boo
 
 def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc: int, n_glob: int,
                   rank: int, world: int, group=None, w_row: float = 1.0, w_col: float = 1.0,
-                  need_i: bool = True, need_t: bool = True, need_scale: bool = True):
-    """(dI_loc, dT_loc, dscale) of the global loss; operands are the backward copies."""
+                  need_i: bool = True, need_t: bool = True, need_scale: bool = True,
+                  out_mul=None, out_dtypes=(torch.float32, torch.float32)):
+    """(dI_loc, dT_loc, dscale) of the global loss; operands are the backward copies.
+
+    ``out_mul`` (device scalar) multiplies dI and dT (not dscale); where a gradient is final on this
+    rank the kernel epilogue applies it and writes ``out_dtypes`` directly."""
     lo = rank * n_loc
     d_i = d_t = ds = None
     if need_i or need_scale:
         d_i, ds = ops.grad(i_loc_op, t_all_op, r_stats, c_stats, scale, -lo, n_glob, w_row, w_col,
-                           need_scale)
+                           need_scale, out_mul, out_dtypes[0])
         if not need_i:
             d_i = None
     if need_t:
-        d_t_all, ds_t = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col, w_row,
-                                 need_scale and ds is None)
-        if ds is None:
-            ds = ds_t
-        if world > 1:
+        if world > 1:   # partial over the local images: fp32 through the reduce-scatter
+            d_t_all, ds_t = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col,
+                                     w_row, need_scale and ds is None, None, torch.float32)
             d_t = torch.empty((n_loc,) + tuple(d_t_all.shape[1:]), dtype=d_t_all.dtype,
                               device=d_t_all.device)
             _dist().reduce_scatter_tensor(d_t, d_t_all.contiguous(), group=group)
+            if out_mul is not None:
+                d_t = d_t * out_mul
         else:
-            d_t = d_t_all
+            d_t, ds_t = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col,
+                                 w_row, need_scale and ds is None, out_mul, out_dtypes[1])
+        if ds is None:
+            ds = ds_t
     if need_scale and world > 1:
         _dist().all_reduce(ds, group=group)
     return d_i, d_t, ds
