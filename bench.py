@@ -52,61 +52,72 @@ def measured_peaks():
 # clocks
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every ~10 ms DURING the timed region (NVML in a thread;
+    falls back to one `nvidia-smi` query when pynvml is unavailable)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = False
+        self._thread = None
+
+    def _run(self):
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.gpu_index
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.gpu_index])
+            except Exception:
+                pass
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        while not self._stop:
+            try:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        import threading
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml  # noqa: F401
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._thread = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        try:
-            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
-            os.unlink(self.path)
-        except Exception:
-            return out
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            if len(r) < 9:
-                continue
+        if self._thread is not None:
+            self._stop = True
+            self._thread.join(timeout=2)
+        if not self.samples:
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, r[5:9]):
-                if val.strip().lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            # samples under load = upper half of the distribution (idle samples bracket the region)
-            sm_sorted = sorted(sm)
-            loaded = sm_sorted[len(sm_sorted) // 2:]
-            out["sm_mhz"] = loaded[len(loaded) // 2]
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+                r = subprocess.run(["nvidia-smi", f"--id={self.gpu_index}",
+                                    "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=10).stdout.strip().split(", ")
+                out["sm_mhz"], out["sm_max_mhz"], out["samples"] = float(r[0]), float(r[1]), 1
+            except Exception:
+                pass
+            return out
+        sm = sorted(self.samples)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_min_mhz"] = sm[0]
+        out["sm_max_mhz"] = self.max_mhz
+        out["samples"] = len(sm)
+        out["reasons"] = sorted(self.reasons)
         return out
 
 
@@ -243,7 +254,6 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
     launches0 = lib.vlpclip_launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)

@@ -35,6 +35,10 @@ const char* vlpclip_last_error(void);
 /* number of SMs of the current device (grid sizing / workspace sizing) */
 int vlpclip_sm_count(void);
 
+/* cap the number of SMs the persistent kernels occupy (0 = all); returns the effective count.
+ * Used by the sharded variant to leave a few SMs to overlapping NCCL kernels. */
+int vlpclip_set_sm_limit(int n_sms);
+
 /* kernels launched by this library so far in this process (bench.py: gpu_launches) */
 unsigned long long vlpclip_launch_count(void);
 

@@ -85,6 +85,18 @@ inline int sm_count() {
   return n;
 }
 
+// optional cap on the SMs the persistent kernels occupy (0 = all): leaves room for NCCL kernels
+// that overlap with the backward in the sharded variant
+inline int& sm_limit() {
+  static int n = 0;
+  return n;
+}
+inline int usable_sms() {
+  const int n = sm_count();
+  const int lim = sm_limit();
+  return (lim > 0 && lim < n) ? lim : n;
+}
+
 inline int check_device_sm100() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(-6, "no CUDA device");

@@ -667,7 +667,7 @@ static void pick_chunks_pairs(int n_row_blocks, int total_tiles, int n_pairs, in
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 static int n_pairs_of_device() {
-  const int n = sm_count();
+  const int n = usable_sms();
   return n > 1 ? n / 2 : 74;   // no device (host-side size queries): assume a B200
 }
 

@@ -474,6 +474,10 @@ int vlpclip_version(void) { return VLPCLIP_VERSION; }
 const char* vlpclip_last_error(void) { return err_buf(); }
 int vlpclip_sm_count(void) { return sm_count(); }
 unsigned long long vlpclip_launch_count(void) { return launch_counter(); }
+int vlpclip_set_sm_limit(int n_sms) {
+  sm_limit() = n_sms > 0 ? n_sms : 0;
+  return usable_sms();
+}
 
 int vlpclip_cast_bf16_to_f16(const void* src, void* dst, size_t n, void* stream) {
   if (n == 0) return 0;
@@ -523,7 +527,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   p.kblocks = (d + 63) / 64;
   p.total_tiles = (n_cols + 127) / 128;
   p.n_row_blocks = (n_rows + 127) / 128;
-  const int nsm = sm_count();
+  const int nsm = usable_sms();
   pick_chunks(p.n_row_blocks, p.total_tiles, nsm, &p.n_chunks, &p.tiles_per_chunk);
   p.diag_shift = diag_shift;
   p.scale = scale;

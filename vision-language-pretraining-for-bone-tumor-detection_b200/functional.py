@@ -30,6 +30,18 @@ EXACT_COLUMNS = os.environ.get("VLP_B200_EXACT_COLUMNS", "0") == "1"
 # ----------------------------------------------------------------------------------------------
 # helpers
 # ----------------------------------------------------------------------------------------------
+_SM_RESERVED = False
+
+
+def _reserve_sms_for_collectives(n_free: int = int(os.environ.get("VLP_B200_NCCL_SMS", "4"))):
+    """Sharded mode: keep a few SMs out of the persistent kernels so NCCL can overlap with them."""
+    global _SM_RESERVED
+    if not _SM_RESERVED:
+        lib = _lib.load()
+        lib.vlpclip_set_sm_limit(max(2, lib.vlpclip_sm_count() - n_free))
+        _SM_RESERVED = True
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -254,6 +266,8 @@ class _FusedClipLoss(torch.autograd.Function):
         if t_bf16 is None:
             t_bf16 = text_embeddings.detach().to(torch.bfloat16).contiguous()
 
+        if group is not None and sharded.group_info(group)[0] > 1:
+            _reserve_sms_for_collectives()
         plan = sharded.forward_plan(CudaOps, i_bf16, t_bf16, scale, group,
                                     exact_columns=EXACT_COLUMNS)
         world = plan["world"]

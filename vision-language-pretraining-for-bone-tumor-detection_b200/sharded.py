@@ -101,25 +101,51 @@ def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc
     rank the kernel epilogue applies it and writes ``out_dtypes`` directly."""
     lo = rank * n_loc
     d_i = d_t = ds = None
-    if need_i or need_scale:
-        d_i, ds = ops.grad(i_loc_op, t_all_op, r_stats, c_stats, scale, -lo, n_glob, w_row, w_col,
-                           need_scale, out_mul, out_dtypes[0])
+    pending = None
+    if need_t and world > 1:
+        # dT_all partial over the local images first, so that its fp32 reduce-scatter (the largest
+        # message of the step, N*D*4 bytes per rank) runs on a side stream under the dI kernel
+        d_t_all, ds = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col, w_row,
+                               need_scale, None, torch.float32)
+        d_t = torch.empty((n_loc,) + tuple(d_t_all.shape[1:]), dtype=d_t_all.dtype,
+                          device=d_t_all.device)
+        if d_t_all.is_cuda and (need_i or need_scale):
+            main = torch.cuda.current_stream()
+            side = _side_stream(d_t_all.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _dist().reduce_scatter_tensor(d_t, d_t_all, group=group)
+            d_t_all.record_stream(side)
+            d_t.record_stream(side)
+            pending = side
+        else:
+            _dist().reduce_scatter_tensor(d_t, d_t_all.contiguous(), group=group)
+    if need_i or (need_scale and ds is None):
+        d_i, ds_i = ops.grad(i_loc_op, t_all_op, r_stats, c_stats, scale, -lo, n_glob, w_row, w_col,
+                             need_scale and ds is None, out_mul, out_dtypes[0])
+        if ds is None:
+            ds = ds_i
         if not need_i:
             d_i = None
-    if need_t:
-        if world > 1:   # partial over the local images: fp32 through the reduce-scatter
-            d_t_all, ds_t = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col,
-                                     w_row, need_scale and ds is None, None, torch.float32)
-            d_t = torch.empty((n_loc,) + tuple(d_t_all.shape[1:]), dtype=d_t_all.dtype,
-                              device=d_t_all.device)
-            _dist().reduce_scatter_tensor(d_t, d_t_all.contiguous(), group=group)
-            if out_mul is not None:
-                d_t = d_t * out_mul
-        else:
-            d_t, ds_t = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col,
-                                 w_row, need_scale and ds is None, out_mul, out_dtypes[1])
+    if need_t and world == 1:
+        d_t, ds_t = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col, w_row,
+                             need_scale and ds is None, out_mul, out_dtypes[1])
         if ds is None:
             ds = ds_t
+    if pending is not None:
+        torch.cuda.current_stream().wait_stream(pending)
+    if need_t and world > 1 and out_mul is not None:
+        d_t = d_t * out_mul
     if need_scale and world > 1:
         _dist().all_reduce(ds, group=group)
     return d_i, d_t, ds
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
