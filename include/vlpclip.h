@@ -15,6 +15,9 @@
  *   - return value 0 = ok, negative = error; vlpclip_last_error() returns a thread-local message;
  *   - the N x N logit matrix is never written to global memory by any entry point.
  *
+ * `scale` is always a DEVICE pointer to one fp32 value s = clamp(exp(logit_scale), max=100)
+ * (VisionLanguageModule.py:456-457): the host never needs the temperature, so a training step
+ * issues no host<->device synchronisation and can be captured in a CUDA graph.
  * "log2 domain": running maxima `m` and sums `l` describe  sum_j exp(S_ij) = l * 2^m .
  */
 #ifndef VLPCLIP_H_
@@ -59,8 +62,9 @@ int vlpclip_cast_bf16_to_f16(const void* src_bf16, void* dst_f16, size_t n_elems
  */
 size_t vlpclip_lse_workspace_bytes(int n_rows, int n_cols, int d);
 int vlpclip_lse_fwd(const void* x_bf16, int ldx, const void* y_bf16, int ldy, int n_rows,
-                    int n_cols, int d, float scale, int diag_shift, float* row_max, float* row_l,
-                    float* diag, void* workspace, size_t workspace_bytes, void* stream);
+                    int n_cols, int d, const float* scale, int diag_shift, float* row_max,
+                    float* row_l, float* diag, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* Same sweep, but ALSO the statistics of the columns of S over the given rows (one pass over
  * the logits instead of two): col_max[j] / col_l[j] ([n_cols] fp32) follow the (max, l) convention
@@ -71,7 +75,7 @@ int vlpclip_lse_fwd(const void* x_bf16, int ldx, const void* y_bf16, int ldy, in
  * Replaces VisionLanguageModule.py:459 + the log-sum-exp halves of :550 AND :551. */
 size_t vlpclip_lse_fused_workspace_bytes(int n_rows, int n_cols, int d);
 int vlpclip_lse_fwd_fused(const void* x_bf16, int ldx, const void* y_bf16, int ldy, int n_rows,
-                          int n_cols, int d, float scale, int diag_shift, float* row_max,
+                          int n_cols, int d, const float* scale, int diag_shift, float* row_max,
                           float* row_l, float* diag, float* col_max, float* col_l, void* workspace,
                           size_t workspace_bytes, void* stream);
 
@@ -84,8 +88,8 @@ int vlpclip_lse_fwd_fused(const void* x_bf16, int ldx, const void* y_bf16, int l
  *   out_loss lse - scale*diag  (per-row cross-entropy, log1p-accurate when the positive dominates;
  *            requires diag) */
 int vlpclip_lse_merge(const float* part_max, const float* part_l, const float* diag, int nparts,
-                      int n, float scale, float* lse, float* out_max, float* out_l, float* out_lg2l,
-                      float* out_q, float* out_loss, void* stream);
+                      int n, const float* scale, float* lse, float* out_max, float* out_l,
+                      float* out_lg2l, float* out_q, float* out_loss, void* stream);
 
 /* out2[0] = sum_i row_loss[i], out2[1] = sum_i col_loss[i] over n entries (either may be NULL);
  * single block, fixed order (reproducible). The caller divides by the global batch size
@@ -109,7 +113,7 @@ int vlpclip_loss_reduce(const float* row_loss, const float* col_loss, int n, flo
 size_t vlpclip_grad_workspace_bytes(int n_rows, int n_cols, int d);
 int vlpclip_grad(const void* x_f16, int ldx, const void* y_f16, int ldy, const float* x_max,
                  const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
-                 const float* y_q, int n_rows, int n_cols, int d, float scale, int diag_shift,
+                 const float* y_q, int n_rows, int n_cols, int d, const float* scale, int diag_shift,
                  int n_global, float w_row, float w_col, const float* out_mul, int dx_bf16, void* dx,
                  float* dscale, void* workspace, size_t workspace_bytes, void* stream);
 

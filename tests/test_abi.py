@@ -48,7 +48,7 @@ def test_version_and_error_string_without_gpu():
     assert lib.vlpclip_grad_workspace_bytes(256, 256, 512) > 0
     assert lib.vlpclip_lse_workspace_bytes(0, 256, 512) == 0
     # argument validation happens before any CUDA call and reports through last_error
-    rc = lib.vlpclip_lse_merge(None, None, None, 0, 0, 1.0, None, None, None, None, None, None, None)
+    rc = lib.vlpclip_lse_merge(None, None, None, 0, 0, None, None, None, None, None, None, None, None)
     assert rc == -1 and b"empty" in lib.vlpclip_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc, "lse_merge")

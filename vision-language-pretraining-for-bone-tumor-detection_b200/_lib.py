@@ -21,18 +21,18 @@ _SIGNATURES = {
     "vlpclip_set_sm_limit": (c_int, [c_int]),
     "vlpclip_cast_bf16_to_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vlpclip_lse_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "vlpclip_lse_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
+    "vlpclip_lse_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vlpclip_lse_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
-    "vlpclip_lse_fwd_fused": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
+    "vlpclip_lse_fwd_fused": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_void_p]),
-    "vlpclip_lse_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p,
+    "vlpclip_lse_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlpclip_loss_reduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "vlpclip_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlpclip_grad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                             c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
+                             c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                              c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                              c_size_t, c_void_p]),
     "vlpclip_project_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -55,8 +55,8 @@ struct GradParams {
   int n_rows, n_cols, d;
   int kblocks, total_tiles, tiles_per_chunk, n_chunks, n_row_blocks;
   int diag_shift;
-  float scale_log2;
-  float out_scale;      // scale / (2 n_global) / 2^13
+  const float* scale_ptr;  // device scalar s
+  float out_scale;      // 1 / (2 n_global) / 2^13   (multiplied by s in the epilogue)
   void* dx;             // [n_rows, d] final output (n_chunks == 1; fp32 or bf16) or fp32 per-chunk
                         // partials [n_chunks][n_rows, d]
   int dx_bf16;          // final output dtype when written by this kernel
@@ -192,6 +192,8 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   const int n_items = p.n_row_blocks * p.n_chunks;
+  const float scale_dev = __ldg(p.scale_ptr);
+  const float scale_log2 = scale_dev * kLog2e;
 
   if (rank == 0) {
     // =====================================================================================
@@ -335,17 +337,17 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
             const float4* yc4 = reinterpret_cast<const float4*>(p.yc + col0);
             float acc = 0.f;   // carries the 2^13 tile scale
             if (any_diag)
-              softmax_tile_fast<true>(v, yc4, xmax, xlg - 13.f, xr, p.scale_log2, diag_val * G_SCALE,
+              softmax_tile_fast<true>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, diag_val * G_SCALE,
                                       diag_j, out, acc);
             else
-              softmax_tile_fast<false>(v, yc4, xmax, xlg - 13.f, xr, p.scale_log2, 0.f, diag_j, out,
+              softmax_tile_fast<false>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, 0.f, diag_j, out,
                                        acc);
             ds_acc = fmaf(acc, 1.0f / G_SCALE, ds_acc);
           } else if (any_diag) {
-            softmax_tile<true>(v, ymax4, ylg4, xmax, xlg, p.scale_log2, diag_val, diag_j, out,
+            softmax_tile<true>(v, ymax4, ylg4, xmax, xlg, scale_log2, diag_val, diag_j, out,
                                ds_acc);
           } else {
-            softmax_tile<false>(v, ymax4, ylg4, xmax, xlg, p.scale_log2, 0.f, diag_j, out, ds_acc);
+            softmax_tile<false>(v, ymax4, ylg4, xmax, xlg, scale_log2, 0.f, diag_j, out, ds_acc);
           }
 
           // stage the fp16 G tile (K-major, 128B swizzle) and push it to the consumer CTA
@@ -471,7 +473,8 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         tc_fence_after();
         const int chunk = item / p.n_row_blocks;
         const bool final_out = p.n_chunks == 1;
-        const float mulv = (final_out && p.out_mul) ? p.out_scale * __ldg(p.out_mul) : p.out_scale;
+        const float mulv =
+            scale_dev * ((final_out && p.out_mul) ? p.out_scale * __ldg(p.out_mul) : p.out_scale);
         const size_t roff = (size_t)chunk * p.chunk_stride + (size_t)(row < p.n_rows ? row : 0) * p.d;
         float* orow = reinterpret_cast<float*>(p.dx) + roff;
         __nv_bfloat16* orow_b = reinterpret_cast<__nv_bfloat16*>(p.dx) + roff;
@@ -529,8 +532,9 @@ constexpr int RANGE_BLOCKS = 32;
 __global__ void lse_range_kernel(const float* __restrict__ xmax, const float* __restrict__ xlg,
                                  int nx, float log2wx, const float* __restrict__ ymax,
                                  const float* __restrict__ ylg, int ny, float log2wy,
-                                 float scale_log2, float* __restrict__ part) {
+                                 const float* __restrict__ scale_ptr, float* __restrict__ part) {
   __shared__ float smin[256], smax[256];
+  const float scale_log2 = __ldg(scale_ptr) * kLog2e;
   float lo = INFINITY, hi = -INFINITY;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx + ny; i += gridDim.x * blockDim.x) {
     const float e = i < nx ? fmaf(scale_log2, xmax[i], xlg[i] - log2wx)
@@ -574,11 +578,13 @@ __device__ __forceinline__ void lse_range_finish(const float* __restrict__ part,
 // weight w >= 0 is folded in as lg2l - log2(w) (w * 2^e = 2^(e + log2 w)).  fac = 2^(sign*(e - C))
 // with e = k*max + lg2l is the fast-path row (sign +1) / column (sign -1) factor, 0 when padded.
 __global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __restrict__ lg, int n,
-                                 int n_pad, float log2w, float scale_log2, float sign,
+                                 int n_pad, float log2w, const float* __restrict__ scale_ptr,
+                                 float sign,
                                  const float* __restrict__ range_part, int force_slow,
                                  int* __restrict__ fast_flag, float* __restrict__ mx_out,
                                  float* __restrict__ lg_out, float* __restrict__ fac_out) {
   __shared__ float c_sh;
+  const float scale_log2 = __ldg(scale_ptr) * kLog2e;
   if (threadIdx.x == 0) {
     float c;
     int fast;
@@ -694,19 +700,20 @@ size_t vlpclip_grad_workspace_bytes(int n_rows, int n_cols, int d) {
 int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_max,
                  const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
                  const float* y_q, int n_rows,
-                 int n_cols, int d, float scale, int diag_shift, int n_global, float w_row,
+                 int n_cols, int d, const float* scale, int diag_shift, int n_global, float w_row,
                  float w_col, const float* out_mul, int dx_bf16, void* dx, float* dscale,
                  void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "grad: empty problem (%d x %d)", n_rows, n_cols);
-  if (!x || !y || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q || !dx || !workspace)
+  if (!x || !y || !scale || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q || !dx ||
+      !workspace)
     return fail(-1, "grad: null pointer");
   if (d <= 0 || d % 8 != 0 || d > 512)
     return fail(-1, "grad: embedding dim %d unsupported (need a multiple of 8, <= 512)", d);
   if (ldx % 8 != 0 || ldy % 8 != 0) return fail(-1, "grad: row strides must be multiples of 8");
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(dx) & 15) != 0)
     return fail(-1, "grad: X and dX must be 16-byte aligned");
-  if (!(scale > 0.f) || n_global <= 0) return fail(-1, "grad: bad scale / n_global");
+  if (n_global <= 0) return fail(-1, "grad: bad n_global");
   if (!(w_row >= 0.f) || !(w_col >= 0.f) || !(w_row + w_col > 0.f))
     return fail(-1, "grad: direction weights must be >= 0 and not both zero");
   int rc = check_device_sm100();
@@ -715,7 +722,7 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
     return fail(-1, "grad: workspace too small (%zu < %zu)", workspace_bytes,
                 grad_ws_bytes(n_rows, n_cols, d));
 
-  GradParams p;
+  GradParams p = {};
   p.x = (const __half*)x;
   p.ldx = ldx;
   p.n_rows = n_rows;
@@ -727,12 +734,12 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   const int n_pairs = n_pairs_of_device();
   pick_chunks_pairs(p.n_row_blocks, p.total_tiles, n_pairs, &p.n_chunks, &p.tiles_per_chunk);
   p.diag_shift = diag_shift;
-  p.scale_log2 = scale * kLog2e;
   p.w_row = w_row;
   p.w_col = w_col;
   p.xq = x_q;
   p.yq = y_q;
-  p.out_scale = scale / (2.0f * (float)n_global) / G_SCALE;
+  p.scale_ptr = scale;
+  p.out_scale = 1.0f / (2.0f * (float)n_global) / G_SCALE;
 
   uint8_t* ws = (uint8_t*)workspace;
   const int npx = p.n_row_blocks * 128, npy = p.total_tiles * 128;
@@ -769,14 +776,14 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   const float l2wr = log2f(w_row), l2wc = log2f(w_col);
   const int force_slow = (w_row == 0.f || w_col == 0.f) ? 1 : 0;
   lse_range_kernel<<<RANGE_BLOCKS, 256, 0, stream>>>(x_max, x_lg2l, n_rows, l2wr, y_max, y_lg2l,
-                                                     n_cols, l2wc, p.scale_log2, range_part);
+                                                     n_cols, l2wc, scale, range_part);
   VLP_COUNT_LAUNCH(1);
   stats_pad_kernel<<<(npx + 255) / 256, 256, 0, stream>>>(x_max, x_lg2l, n_rows, npx, l2wr,
-                                                          p.scale_log2, 1.f, range_part, force_slow,
+                                                          scale, 1.f, range_part, force_slow,
                                                           fast_flag, xmax, xlg, xr);
   VLP_COUNT_LAUNCH(1);
   stats_pad_kernel<<<(npy + 255) / 256, 256, 0, stream>>>(y_max, y_lg2l, n_cols, npy, l2wc,
-                                                          p.scale_log2, -1.f, range_part, force_slow,
+                                                          scale, -1.f, range_part, force_slow,
                                                           fast_flag, ymax, ylg, yc);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());

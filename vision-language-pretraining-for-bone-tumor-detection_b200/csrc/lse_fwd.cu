@@ -42,8 +42,7 @@ struct LseParams {
   int n_chunks;
   int n_row_blocks;
   int diag_shift;       // delta_ij = 1 iff i == j + diag_shift
-  float scale;          // s
-  float scale_log2;     // s * log2(e)
+  const float* scale_ptr;  // device scalar s = clamp(exp(logit_scale), max=100)
   float* part_m;        // [n_chunks * FWD_CG][n_rows] raw (unscaled) running max of <X_i, Y_j>
   float* part_l;
   float* diag;          // [n_rows]: raw <X_i, Y_{i - diag_shift}>
@@ -101,6 +100,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
   const uint32_t tmem = bars->tmem_base;
 
   const int n_items = p.n_row_blocks * p.n_chunks;
+  const float scale_log2 = __ldg(p.scale_ptr) * kLog2e;   // k = s * log2(e), device-side scalar
 
   if (warp == 0) {
     // ================= TMA producer (whole warp converged, one elected lane issues) ==========
@@ -250,13 +250,13 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           if (row_ok && dcol >= col0 && dcol < col0 + FWD_CPT) p.diag[row] = dv;
         }
         const float mraw_new = fmaxf(mraw_run, mx);
-        const float m_new = mraw_new * p.scale_log2;  // log2-domain reference of this row
+        const float m_new = mraw_new * scale_log2;  // log2-domain reference of this row
         if (mraw_new != -INFINITY) {
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int j = 0; j < FWD_CPT; j += 2) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2, -m_new));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -m_new));
+            const float e0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2, -m_new));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2, -m_new));
             s0 += e0;
             s1 += e1;
             if (kCols) {
@@ -341,12 +341,13 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
 // diag == nullptr: no positive pair in these columns (t = 0).
 __global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
                                  const float* __restrict__ diag, int nparts, int n,
-                                 float scale_log2, float* __restrict__ lse,
+                                 const float* __restrict__ scale_ptr, float* __restrict__ lse,
                                  float* __restrict__ out_max, float* __restrict__ out_l,
                                  float* __restrict__ out_lg2l, float* __restrict__ out_q,
                                  float* __restrict__ out_loss) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const float scale_log2 = __ldg(scale_ptr) * kLog2e;
   float m = -INFINITY;
   for (int q = 0; q < nparts; ++q) m = fmaxf(m, part_m[(size_t)q * n + i]);
   const float m2 = m * scale_log2;
@@ -378,10 +379,12 @@ __global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* 
 // Fused forward: merge the per-row-block column partials (log2-domain reference, l) of one column
 // in fixed order and convert to the (raw max, l) convention of lse_merge_kernel.
 __global__ void col_merge_kernel(const float* __restrict__ col_ref, const float* __restrict__ col_l,
-                                 int n_row_blocks, size_t stride, int n_cols, float scale_log2,
+                                 int n_row_blocks, size_t stride, int n_cols,
+                                 const float* __restrict__ scale_ptr,
                                  float* __restrict__ out_max, float* __restrict__ out_l) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_cols) return;
+  const float scale_log2 = __ldg(scale_ptr) * kLog2e;
   float M = -INFINITY;
   for (int r = 0; r < n_row_blocks; ++r) M = fmaxf(M, col_ref[(size_t)r * stride + j]);
   float L = 0.f;
@@ -498,12 +501,13 @@ size_t vlpclip_lse_workspace_bytes(int n_rows, int n_cols, int d) {
 }
 
 static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,
-                        int d, float scale, int diag_shift, float* row_max, float* row_l, float* diag,
+                        int d, const float* scale, int diag_shift, float* row_max, float* row_l,
+                        float* diag,
                         float* col_max, float* col_l, void* workspace, size_t workspace_bytes,
                         cudaStream_t stream) {
   const bool fused = col_max != nullptr;
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "lse_fwd: empty problem (%d x %d)", n_rows, n_cols);
-  if (!x || !y || !row_max || !row_l || !diag || !workspace || (fused && !col_l))
+  if (!x || !y || !scale || !row_max || !row_l || !diag || !workspace || (fused && !col_l))
     return fail(-1, "lse_fwd: null pointer");
   if (d <= 0 || d % 8 != 0 || d > 512)
     return fail(-1, "lse_fwd: embedding dim %d unsupported (need a multiple of 8, <= 512)", d);
@@ -511,14 +515,13 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
     return fail(-1, "lse_fwd: row strides must be multiples of 8 elements");
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0)
     return fail(-1, "lse_fwd: X must be 16-byte aligned");
-  if (!(scale > 0.f)) return fail(-1, "lse_fwd: scale must be positive");
   int rc = check_device_sm100();
   if (rc) return rc;
   const size_t need = fused ? lse_fused_ws_bytes(n_rows, n_cols) : lse_ws_bytes(n_rows, n_cols);
   if (workspace_bytes < need)
     return fail(-1, "lse_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
 
-  LseParams p;
+  LseParams p = {};
   p.x = (const __nv_bfloat16*)x;
   p.ldx = ldx;
   p.n_rows = n_rows;
@@ -530,8 +533,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   const int nsm = usable_sms();
   pick_chunks(p.n_row_blocks, p.total_tiles, nsm, &p.n_chunks, &p.tiles_per_chunk);
   p.diag_shift = diag_shift;
-  p.scale = scale;
-  p.scale_log2 = scale * kLog2e;
+  p.scale_ptr = scale;
   const int nparts = p.n_chunks * FWD_CG;
   p.part_m = (float*)workspace;
   p.part_l = p.part_m + (size_t)nparts * n_rows;
@@ -566,13 +568,13 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   lse_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_m, p.part_l, nullptr, nparts,
-                                                             n_rows, p.scale_log2, nullptr, row_max,
+                                                             n_rows, scale, nullptr, row_max,
                                                              row_l, nullptr, nullptr, nullptr);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   if (fused) {
     col_merge_kernel<<<(n_cols + 127) / 128, 128, 0, stream>>>(
-        p.col_ref, p.col_l, p.n_row_blocks, col_stride, n_cols, p.scale_log2, col_max, col_l);
+        p.col_ref, p.col_l, p.n_row_blocks, col_stride, n_cols, scale, col_max, col_l);
     VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
   }
@@ -580,7 +582,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
 }
 
 int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols, int d,
-                    float scale, int diag_shift, float* row_max, float* row_l, float* diag,
+                    const float* scale, int diag_shift, float* row_max, float* row_l, float* diag,
                     void* workspace, size_t workspace_bytes, void* stream_) {
   return lse_fwd_impl(x, ldx, y, ldy, n_rows, n_cols, d, scale, diag_shift, row_max, row_l, diag,
                       nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_);
@@ -593,7 +595,7 @@ size_t vlpclip_lse_fused_workspace_bytes(int n_rows, int n_cols, int d) {
 }
 
 int vlpclip_lse_fwd_fused(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,
-                          int d, float scale, int diag_shift, float* row_max, float* row_l,
+                          int d, const float* scale, int diag_shift, float* row_max, float* row_l,
                           float* diag, float* col_max, float* col_l, void* workspace,
                           size_t workspace_bytes, void* stream_) {
   if (!col_max || !col_l) return fail(-1, "lse_fwd_fused: null column outputs");
@@ -602,13 +604,14 @@ int vlpclip_lse_fwd_fused(const void* x, int ldx, const void* y, int ldy, int n_
 }
 
 int vlpclip_lse_merge(const float* part_max, const float* part_l, const float* diag, int nparts,
-                      int n, float scale, float* lse, float* out_max, float* out_l, float* out_lg2l,
+                      int n, const float* scale, float* lse, float* out_max, float* out_l,
+                      float* out_lg2l,
                       float* out_q, float* out_loss, void* stream) {
   if (n <= 0 || nparts <= 0) return fail(-1, "lse_merge: empty input");
-  if (!part_max || !part_l) return fail(-1, "lse_merge: null pointer");
+  if (!part_max || !part_l || !scale) return fail(-1, "lse_merge: null pointer");
   if (out_loss && !diag) return fail(-1, "lse_merge: per-row loss needs the positive-pair logits");
   lse_merge_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      part_max, part_l, diag, nparts, n, scale * kLog2e, lse, out_max, out_l, out_lg2l, out_q,
+      part_max, part_l, diag, nparts, n, scale, lse, out_max, out_l, out_lg2l, out_q,
       out_loss);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());

@@ -64,6 +64,14 @@ def _as_2d_contig(t: torch.Tensor, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def as_scale_tensor(scale, device) -> torch.Tensor:
+    """fp32 device scalar [1] holding s; accepts a python number or a tensor (no host sync for the
+    latter)."""
+    if isinstance(scale, torch.Tensor):
+        return scale.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+    return torch.full((1,), float(scale), dtype=torch.float32, device=device)
+
+
 def cast_bf16_to_f16(src: torch.Tensor) -> torch.Tensor:
     """fp16 copy of bf16 embeddings (operands of the backward GEMMs)."""
     _require_cuda(src, "src")
@@ -92,13 +100,14 @@ def lse_stats(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shi
     n_cols = y.shape[0]
     lib = _lib.load()
     dev = x.device
+    sc = as_scale_tensor(scale, dev)
     row_max = torch.empty(n_rows, dtype=torch.float32, device=dev)
     row_l = torch.empty(n_rows, dtype=torch.float32, device=dev)
     diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
     nbytes = lib.vlpclip_lse_workspace_bytes(n_rows, n_cols, d)
     ws = _ws(nbytes, dev)
     rc = lib.vlpclip_lse_fwd(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows, n_cols, d,
-                             float(scale), int(diag_shift), row_max.data_ptr(), row_l.data_ptr(),
+                             sc.data_ptr(), int(diag_shift), row_max.data_ptr(), row_l.data_ptr(),
                              diag.data_ptr(), ws.data_ptr(), nbytes, _stream())
     _lib.check(rc, "lse_fwd")
     return row_max, row_l, diag
@@ -119,6 +128,7 @@ def lse_stats_fused(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, di
     n_cols = y.shape[0]
     lib = _lib.load()
     dev = x.device
+    sc = as_scale_tensor(scale, dev)
     row_max = torch.empty(n_rows, dtype=torch.float32, device=dev)
     row_l = torch.empty(n_rows, dtype=torch.float32, device=dev)
     diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
@@ -127,7 +137,7 @@ def lse_stats_fused(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, di
     nbytes = lib.vlpclip_lse_fused_workspace_bytes(n_rows, n_cols, d)
     ws = _ws(nbytes, dev)
     rc = lib.vlpclip_lse_fwd_fused(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows,
-                                   n_cols, d, float(scale), int(diag_shift), row_max.data_ptr(),
+                                   n_cols, d, sc.data_ptr(), int(diag_shift), row_max.data_ptr(),
                                    row_l.data_ptr(), diag.data_ptr(), col_max.data_ptr(),
                                    col_l.data_ptr(), ws.data_ptr(), nbytes, _stream())
     _lib.check(rc, "lse_fwd_fused")
@@ -147,6 +157,7 @@ def merge_stats(part_max: torch.Tensor, part_l: torch.Tensor, diag: Optional[tor
     nparts, n = part_max.shape
     dev = part_max.device
     lib = _lib.load()
+    sc = as_scale_tensor(scale, dev)
     out_max = torch.empty(n, dtype=torch.float32, device=dev)
     out_lg = torch.empty(n, dtype=torch.float32, device=dev)
     out_q = torch.empty(n, dtype=torch.float32, device=dev)
@@ -154,7 +165,7 @@ def merge_stats(part_max: torch.Tensor, part_l: torch.Tensor, diag: Optional[tor
     lse = torch.empty(n, dtype=torch.float32, device=dev) if want_lse else None
     rc = lib.vlpclip_lse_merge(part_max.data_ptr(), part_l.data_ptr(),
                                diag.data_ptr() if diag is not None else None, nparts, n,
-                               float(scale), lse.data_ptr() if want_lse else None,
+                               sc.data_ptr(), lse.data_ptr() if want_lse else None,
                                out_max.data_ptr(), None, out_lg.data_ptr(), out_q.data_ptr(),
                                out_loss.data_ptr() if out_loss is not None else None, _stream())
     _lib.check(rc, "lse_merge")
@@ -182,6 +193,7 @@ def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_globa
     n_rows, d = x_f16.shape
     n_cols = y_f16.shape[0]
     dev = x_f16.device
+    sc = as_scale_tensor(scale, dev)
     assert out_dtype in (torch.float32, torch.bfloat16)
     dx = torch.empty(n_rows, d, dtype=out_dtype, device=dev)
     ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
@@ -190,7 +202,7 @@ def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_globa
     rc = lib.vlpclip_grad(x_f16.data_ptr(), x_f16.stride(0), y_f16.data_ptr(), y_f16.stride(0),
                           x_stats[0].data_ptr(), x_stats[1].data_ptr(), x_stats[2].data_ptr(),
                           y_stats[0].data_ptr(), y_stats[1].data_ptr(), y_stats[2].data_ptr(),
-                          n_rows, n_cols, d, float(scale), int(diag_shift), int(n_global),
+                          n_rows, n_cols, d, sc.data_ptr(), int(diag_shift), int(n_global),
                           float(w_row), float(w_col),
                           out_mul.data_ptr() if out_mul is not None else None,
                           1 if out_dtype == torch.bfloat16 else 0, dx.data_ptr(),
@@ -255,11 +267,12 @@ class _FusedClipLoss(torch.autograd.Function):
         if n_loc == 0:
             raise ValueError("empty batch")
 
-        # reference :456-457 -- exp + clamp(max=100); value needed on the host as a launch scalar
-        ls_val = float(logit_scale.detach().double().item())
-        e = math.exp(ls_val)
-        scale = min(e, LOGIT_SCALE_MAX)
-        clamped = e > LOGIT_SCALE_MAX
+        # reference :456-457 -- exp + clamp(max=100), evaluated ON THE DEVICE (no host sync): the
+        # kernels read s through a pointer
+        exp_ls = logit_scale.detach().double().exp().reshape(1)
+        scale = torch.clamp(exp_ls, max=LOGIT_SCALE_MAX).float()
+        # d/dl clamp(e^l, max=100) = e^l if e^l <= 100 else 0
+        dscale_dls = torch.where(exp_ls <= LOGIT_SCALE_MAX, exp_ls, torch.zeros_like(exp_ls)).float()
 
         if i_bf16 is None:
             i_bf16 = image_embeddings.detach().to(torch.bfloat16).contiguous()
@@ -274,7 +287,7 @@ class _FusedClipLoss(torch.autograd.Function):
         ctx.group = group
         ctx.world, ctx.rank = world, plan["rank"]
         ctx.n_loc, ctx.n_glob = n_loc, plan["n_glob"]
-        ctx.scale, ctx.exp_ls, ctx.clamped = scale, e, clamped
+        ctx.scale, ctx.dscale_dls = scale, dscale_dls
         ctx.grad_scale = float(grad_scale)
         ctx.in_dtypes = (image_embeddings.dtype, text_embeddings.dtype, logit_scale.dtype)
         ctx.ls_shape = logit_scale.shape
@@ -321,8 +334,7 @@ class _FusedClipLoss(torch.autograd.Function):
             out_dtypes=(kdt(ctx.in_dtypes[0]), kdt(ctx.in_dtypes[1])))
         d_ls = None
         if need_ls:
-            # d/dl clamp(e^l, max=100) = e^l if e^l <= 100 else 0   (reference :456-457)
-            d_ls = ds * (0.0 if ctx.clamped else ctx.exp_ls)
+            d_ls = ds * ctx.dscale_dls                      # chain rule through exp + clamp (:456-457)
             d_ls = (d_ls * mul).to(ctx.in_dtypes[2]).reshape(ctx.ls_shape)
         if need_i and d_i.dtype != ctx.in_dtypes[0]:
             d_i = d_i.to(ctx.in_dtypes[0])
@@ -442,6 +454,7 @@ def clip_lse_stats(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor
                    logit_scale_value: float):
     """Forward-only helper: (row_lse, col_lse, diag_logit) in natural-log units (no autograd)."""
     s = min(math.exp(float(logit_scale_value)), LOGIT_SCALE_MAX)
+    s = as_scale_tensor(s, image_embeddings.device)
     ib = image_embeddings.detach().to(torch.bfloat16).contiguous()
     tb = text_embeddings.detach().to(torch.bfloat16).contiguous()
     rm, rl, rdiag = lse_stats(ib, tb, s, 0)
