@@ -45,6 +45,10 @@ def _worker(rank, world, port, n, d, ls, out_dir):
                  text_loss=tl.item(), dI=Il.grad.cpu().numpy(), dT=Tl.grad.cpu().numpy(),
                  dl=lsc.grad.item())
     finally:
+        try:
+            VF.release_graphs()
+        except Exception:
+            pass
         dist.destroy_process_group()
 
 

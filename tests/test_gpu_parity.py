@@ -264,3 +264,21 @@ def test_fused_and_exact_column_statistics_agree(VF):
         has = torch.zeros(n_cols, dtype=torch.bool, device=dev)
         has[idx[ok]] = True
         assert torch.allclose(lse_f[has], lse_e[has], rtol=2e-6, atol=2e-5)
+
+
+def test_cuda_graph_path_matches_eager(VF, monkeypatch):
+    """fwd+bwd captured as one CUDA graph (default for sharded runs) vs the eager path."""
+    I, T = O.make_embeddings(700, 128, seed=8)
+    eager = run_fused(VF, I, T, 2.6593)
+    monkeypatch.setattr(VF, "_GRAPH_MODE", "1")
+    VF._GRAPHS.clear()
+    outs = [run_fused(VF, I, T, 2.6593) for _ in range(4)]     # call 1 eager warm-up, 2 captures, 3+ replay
+    I2, T2 = O.make_embeddings(700, 128, seed=9)                # new data through the same graph
+    other = run_fused(VF, I2, T2, 3.0)
+    monkeypatch.setattr(VF, "_GRAPH_MODE", "0")
+    ref2 = O.closed_form(I2.numpy(), T2.numpy(), 3.0)
+    for o in outs:
+        assert o["loss"] == eager["loss"] and o["dl"] == eager["dl"]
+        assert np.array_equal(o["dI"], eager["dI"]) and np.array_equal(o["dT"], eager["dT"])
+    assert_close(other, ref2, ref2["dlogit_scale"])
+    VF._GRAPHS.clear()
