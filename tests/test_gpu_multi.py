@@ -38,9 +38,20 @@ def _worker(rank, world, port, n, d, ls, out_dir):
         Il = I[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
         Tl = T[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
         lsc = torch.tensor([ls], dtype=torch.float64, device=dev, requires_grad=True)
-        loss, il, tl = VF.fused_clip_loss_from_embeddings(Il, Tl, lsc, group=dist.group.WORLD)
-        loss.backward()
-        torch.cuda.synchronize()
+        # 4 steps: the first runs eagerly, the second captures fwd+bwd (kernels + NCCL collectives)
+        # into a CUDA graph, the rest replay it -- results must not change
+        first = None
+        for _ in range(4):
+            Il.grad = Tl.grad = lsc.grad = None
+            loss, il, tl = VF.fused_clip_loss_from_embeddings(Il, Tl, lsc, group=dist.group.WORLD)
+            loss.backward()
+            torch.cuda.synchronize()
+            cur = (loss.item(), Il.grad.clone(), Tl.grad.clone(), lsc.grad.item())
+            if first is None:
+                first = cur
+            else:
+                assert cur[0] == first[0] and cur[3] == first[3]
+                assert torch.equal(cur[1], first[1]) and torch.equal(cur[2], first[2])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss.item(), image_loss=il.item(),
                  text_loss=tl.item(), dI=Il.grad.cpu().numpy(), dT=Tl.grad.cpu().numpy(),
                  dl=lsc.grad.item())
