@@ -20,7 +20,8 @@ def VF():
     return functional
 
 
-@pytest.mark.parametrize("n,fi,ft,d", [(256, 512, 312, 512), (300, 512, 768, 128), (1024, 2048, 312, 256), (64, 512, 312, 32)])
+@pytest.mark.parametrize("n,fi,ft,d", [(256, 512, 312, 512), (300, 512, 768, 128), (1024, 2048, 312, 256), (64, 512, 312, 32),
+                                       (384, 512, 312, 768)])
 def test_head_against_straight_through_oracle(VF, n, fi, ft, d):
     dev = torch.device("cuda:0")
     ls = math.log(1 / 0.07)

@@ -80,6 +80,9 @@ def test_against_reference_golden_vectors(VF, golden_dir, name):
     (2048, 256, 2.6593, 0.35),
     (4096, 512, 2.6593, 0.35),              # BASELINE config 3 size on one GPU
     (4096, 512, 4.6, 0.35),
+    (256, 768, 2.6593, 0.35),               # BASELINE config 5 embedding dim: single S buffer, 2-pass dX
+    (1000, 640, 3.0, 0.35),
+    (2048, 768, 2.6593, 0.35),
 ])
 def test_against_closed_form_oracle(VF, n, d, ls, rho):
     I, T = O.make_embeddings(n, d, rho=rho, seed=42)
@@ -157,8 +160,8 @@ def test_errors_are_raised_not_swallowed(VF):
     with pytest.raises(ValueError):   # embedding dim must be a multiple of 8
         VF.fused_clip_loss_from_embeddings(torch.randn(16, 12, device=dev), torch.randn(16, 12, device=dev),
                                            torch.tensor([2.0], device=dev))
-    with pytest.raises(ValueError):   # > 512 columns do not fit the TMEM accumulator plan yet
-        VF.fused_clip_loss_from_embeddings(torch.randn(16, 768, device=dev), torch.randn(16, 768, device=dev),
+    with pytest.raises(ValueError):   # > 768 columns do not fit the TMEM plan
+        VF.fused_clip_loss_from_embeddings(torch.randn(16, 1024, device=dev), torch.randn(16, 1024, device=dev),
                                            torch.tensor([2.0], device=dev))
 
 

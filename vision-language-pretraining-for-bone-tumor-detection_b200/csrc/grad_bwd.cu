@@ -35,8 +35,8 @@ constexpr int C_STAGE_BYTES = 32768;
 constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
 constexpr int G_SLOT_BYTES = 32768;         // [128 rows x 128 q] fp16
 constexpr int G_SLOTS = 2;
-constexpr uint32_t BWD_TMEM_X = 0;          // producer: X block (fp16 packed) cols [0,256)
-constexpr uint32_t BWD_TMEM_S = 256;        // producer: two S buffers
+constexpr uint32_t BWD_TMEM_X = 0;          // producer: X block (fp16 packed), d/2 columns
+// producer S buffers (128 columns each) at the top of TMEM: two while d <= 512, one for d <= 768
 constexpr float G_SCALE = 8192.f;           // 2^13: keeps softmax tails out of fp16 subnormals
 
 struct GradParams {
@@ -54,6 +54,7 @@ struct GradParams {
   float w_row, w_col;
   int n_rows, n_cols, d;
   int kblocks, total_tiles, tiles_per_chunk, n_chunks, n_row_blocks;
+  int db0, ndb;         // consumer: first 64-column block / number of blocks of dX in this pass
   int diag_shift;
   const float* scale_ptr;  // device scalar s
   float out_scale;      // 1 / (2 n_global) / 2^13   (multiplied by s in the epilogue)
@@ -194,6 +195,8 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
   const int n_items = p.n_row_blocks * p.n_chunks;
   const float scale_dev = __ldg(p.scale_ptr);
   const float scale_log2 = scale_dev * kLog2e;
+  const uint32_t nbuf = p.kblocks <= 8 ? 2u : 1u;
+  const uint32_t tmem_s_col = 512u - nbuf * 128u;
 
   if (rank == 0) {
     // =====================================================================================
@@ -229,10 +232,11 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
         tc_fence_after();
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
-          const uint32_t buf = tile_ctr & 1;
-          mbar_wait(smem_u32(&bars->s_empty[buf]), ((tile_ctr >> 1) & 1) ^ 1);
+          const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+          const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+          mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem + BWD_TMEM_S + buf * 128;
+          const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
           for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
             const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
             const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
@@ -308,14 +312,15 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         float ds_acc = 0.f;
 
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
-          const uint32_t buf = tile_ctr & 1;
-          mbar_wait(smem_u32(&bars->s_full[buf]), (tile_ctr >> 1) & 1);
+          const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+          const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+          mbar_wait(smem_u32(&bars->s_full[buf]), use & 1);
           tc_fence_after();
           uint32_t v[64];
           {
             uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
             uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-            const uint32_t a = tmem + lane_addr + BWD_TMEM_S + buf * 128 + half * 64;
+            const uint32_t a = tmem + lane_addr + tmem_s_col + buf * 128 + half * 64;
             tmem_ld_x32(a, v0);
             tmem_ld_x32(a + 32, v1);
             tmem_ld_wait();
@@ -395,7 +400,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     // =====================================================================================
     // consumer CTA: dX block accumulates in TMEM over the whole column sweep
     // =====================================================================================
-    const int n_nc = (p.kblocks + 3) / 4;  // 256-wide accumulator chunks
+    const int n_nc = (p.ndb + 3) / 4;  // 256-wide accumulator chunks of this pass
     if (warp == 0) {
       uint32_t it = 0;
       for (int item = cluster_id; item < n_items; item += n_clusters) {
@@ -404,7 +409,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
         for (int t = t0; t < t1; ++t)
           for (int nc = 0; nc < n_nc; ++nc) {
-            const int nb = min(4, p.kblocks - nc * 4);
+            const int nb = min(4, p.ndb - nc * 4);
             for (int kh = 0; kh < 2; ++kh, ++it) {
               const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
               mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
@@ -412,7 +417,8 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
                 mbar_expect_tx(smem_u32(&bars->full[st]), nb * 8192);
                 for (int b = 0; b < nb; ++b)
                   tma_load_2d(ring + st * C_STAGE_BYTES + b * 8192, &map_y_mn,
-                              smem_u32(&bars->full[st]), (nc * 4 + b) * 64, t * 128 + kh * 64);
+                              smem_u32(&bars->full[st]), (p.db0 + nc * 4 + b) * 64,
+                              t * 128 + kh * 64);
               }
               __syncwarp();
             }
@@ -434,7 +440,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           tc_fence_after();
           const uint32_t ga = gslots + slot * G_SLOT_BYTES;
           for (int nc = 0; nc < n_nc; ++nc) {
-            const int nb = min(4, p.kblocks - nc * 4);
+            const int nb = min(4, p.ndb - nc * 4);
             const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
             for (int kh = 0; kh < 2; ++kh, ++it) {
               const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
@@ -478,10 +484,12 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         const size_t roff = (size_t)chunk * p.chunk_stride + (size_t)(row < p.n_rows ? row : 0) * p.d;
         float* orow = reinterpret_cast<float*>(p.dx) + roff;
         __nv_bfloat16* orow_b = reinterpret_cast<__nv_bfloat16*>(p.dx) + roff;
-        for (int c = 0; c < p.kblocks * 64; c += 32) {
+        const int cbase = p.db0 * 64;   // first dX column of this pass
+        for (int cc = 0; cc < p.ndb * 64; cc += 32) {
           uint32_t v[32];
-          tmem_ld_x32(tmem + lane_addr + c, v);
+          tmem_ld_x32(tmem + lane_addr + cc, v);
           tmem_ld_wait();
+          const int c = cbase + cc;
           if (row < p.n_rows) {
             if (final_out && p.dx_bf16) {
 #pragma unroll
@@ -708,8 +716,8 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   if (!x || !y || !scale || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q || !dx ||
       !workspace)
     return fail(-1, "grad: null pointer");
-  if (d <= 0 || d % 8 != 0 || d > 512)
-    return fail(-1, "grad: embedding dim %d unsupported (need a multiple of 8, <= 512)", d);
+  if (d <= 0 || d % 8 != 0 || d > 768)
+    return fail(-1, "grad: embedding dim %d unsupported (need a multiple of 8, <= 768)", d);
   if (ldx % 8 != 0 || ldy % 8 != 0) return fail(-1, "grad: row strides must be multiples of 8");
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(dx) & 15) != 0)
     return fail(-1, "grad: X and dX must be 16-byte aligned");
@@ -803,9 +811,18 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   }
   const int n_items = p.n_row_blocks * p.n_chunks;
   const int clusters = n_items < n_pairs ? n_items : n_pairs;
-  grad_pair_kernel<<<clusters * 2, BWD_THREADS, smem, stream>>>(map_k, map_mn, p);
-  VLP_COUNT_LAUNCH(1);
-  VLP_CUDA_OK(cudaGetLastError());
+  // the dX block of a pass must fit the consumer's 512 TMEM columns: d <= 512 in one pass,
+  // 512 < d <= 768 in two passes of half the 64-column blocks each (S is recomputed per pass)
+  const int n_pass = p.kblocks > 8 ? 2 : 1;
+  const int per_pass = (p.kblocks + n_pass - 1) / n_pass;
+  float* ds_keep = p.ds_part;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    p.db0 = pass * per_pass;
+    p.ndb = (p.kblocks - p.db0) < per_pass ? (p.kblocks - p.db0) : per_pass;
+    p.ds_part = pass == 0 ? ds_keep : nullptr;
+    grad_pair_kernel<<<clusters * 2, BWD_THREADS, smem, stream>>>(map_k, map_mn, p);
+    VLP_COUNT_LAUNCH(1);
+  }
   if (p.n_chunks > 1) {
     const size_t n4 = (size_t)n_rows * d / 4;
     int blocks = (int)((n4 + 255) / 256);

@@ -29,8 +29,9 @@ constexpr int FWD_SMW = 16;                  // softmax warps: 4 TMEM lane quart
 constexpr int FWD_CG = FWD_SMW / 4;          // column groups per tile
 constexpr int FWD_CPT = 128 / FWD_CG;        // columns per thread (32)
 constexpr int FWD_THREADS = 64 + FWD_SMW * 32;
-constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: up to 256 columns (d <= 512)
-constexpr uint32_t TMEM_S_COL = 256;    // two S buffers of 128 columns
+constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: d/2 columns (256 at d = 512, 384 at d = 768)
+// S buffers of 128 columns sit at the top of TMEM: two (double buffered) while d <= 512, a single
+// one for 512 < d <= 768 (MMA and softmax of consecutive tiles then serialise)
 
 struct LseParams {
   const __nv_bfloat16* x;
@@ -101,6 +102,8 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
 
   const int n_items = p.n_row_blocks * p.n_chunks;
   const float scale_log2 = __ldg(p.scale_ptr) * kLog2e;   // k = s * log2(e), device-side scalar
+  const uint32_t nbuf = p.kblocks <= 8 ? 2u : 1u;
+  const uint32_t tmem_s_col = 512u - nbuf * 128u;
 
   if (warp == 0) {
     // ================= TMA producer (whole warp converged, one elected lane issues) ==========
@@ -136,10 +139,11 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
       tc_fence_after();
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
-        const uint32_t buf = tile_ctr & 1;
-        mbar_wait(smem_u32(&bars->s_empty[buf]), ((tile_ctr >> 1) & 1) ^ 1);
+        const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+        const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+        mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem + TMEM_S_COL + buf * 128;
+        const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
         for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE, ++it) {
           const uint32_t st = it % FWD_STAGES;
           const uint32_t ph = (it / FWD_STAGES) & 1;
@@ -217,11 +221,12 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       // column holding this row's positive pair (none for padded rows)
       const int dcol = row_ok ? row - p.diag_shift : -1000000000;
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
-        const uint32_t buf = tile_ctr & 1;
-        mbar_wait(smem_u32(&bars->s_full[buf]), (tile_ctr >> 1) & 1);
+        const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+        const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+        mbar_wait(smem_u32(&bars->s_full[buf]), use & 1);
         tc_fence_after();
         uint32_t v[FWD_CPT];
-        tmem_ld_x32(tmem + lane_addr + TMEM_S_COL + buf * 128 + cg * FWD_CPT, v);
+        tmem_ld_x32(tmem + lane_addr + tmem_s_col + buf * 128 + cg * FWD_CPT, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -509,8 +514,8 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "lse_fwd: empty problem (%d x %d)", n_rows, n_cols);
   if (!x || !y || !scale || !row_max || !row_l || !diag || !workspace || (fused && !col_l))
     return fail(-1, "lse_fwd: null pointer");
-  if (d <= 0 || d % 8 != 0 || d > 512)
-    return fail(-1, "lse_fwd: embedding dim %d unsupported (need a multiple of 8, <= 512)", d);
+  if (d <= 0 || d % 8 != 0 || d > 768)
+    return fail(-1, "lse_fwd: embedding dim %d unsupported (need a multiple of 8, <= 768)", d);
   if (ldx % 8 != 0 || ldy % 8 != 0)
     return fail(-1, "lse_fwd: row strides must be multiples of 8 elements");
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0)

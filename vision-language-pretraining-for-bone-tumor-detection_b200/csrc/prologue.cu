@@ -241,6 +241,30 @@ __global__ void normalize_bwd_kernel(const float* __restrict__ emb, const float*
   for (int c = lane; c < d; c += 32) o[c] = (g[c] - e[c] * dot) * inv;
 }
 
+// emb = u / max(||u||, 1e-12) in place (u = emb_f32 on entry), plus the bf16 / fp16 operand copies;
+// used when the embedding dim exceeds the 512 accumulator columns of the fused epilogue
+__global__ void normalize_fwd_kernel(float* __restrict__ emb, __nv_bfloat16* __restrict__ emb_bf16,
+                                     __half* __restrict__ emb_f16, float* __restrict__ inv_norm,
+                                     int n, int d) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float* u = emb + (size_t)row * d;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) ss = fmaf(u[c], u[c], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0) inv_norm[row] = inv;
+  for (int c = lane; c < d; c += 32) {
+    const float e = u[c] * inv;
+    const __nv_bfloat16 b = __float2bfloat16_rn(e);
+    u[c] = e;
+    emb_bf16[(size_t)row * d + c] = b;
+    emb_f16[(size_t)row * d + c] = __float2half_rn(__bfloat162float(b));
+  }
+}
+
 static size_t pg_align(size_t x) { return (x + 255) & ~size_t(255); }
 
 // C[m,n] (+)= A[m,k] * B[n,k]^T with both operands K-major fp32
@@ -294,8 +318,8 @@ int vlpclip_project_normalize_fwd(const float* feat, const float* w, int n, int 
   if (n <= 0 || f <= 0 || d <= 0) return fail(-1, "project: empty problem");
   if (!feat || !w || !emb_f32 || !emb_bf16 || !emb_f16 || !inv_norm || !workspace)
     return fail(-1, "project: null pointer");
-  if (d % 8 != 0 || d > 512)
-    return fail(-1, "project: embedding dim %d unsupported (multiple of 8, <= 512)", d);
+  if (d % 8 != 0 || d > 768)
+    return fail(-1, "project: embedding dim %d unsupported (multiple of 8, <= 768)", d);
   if (f % 4 != 0) return fail(-1, "project: feature dim %d must be a multiple of 4", f);
   int rc = check_device_sm100();
   if (rc) return rc;
@@ -305,6 +329,21 @@ int vlpclip_project_normalize_fwd(const float* feat, const float* w, int n, int 
   launch_transpose(w, wt, f, d, stream);
   VLP_CUDA_OK(cudaGetLastError());
   GemmParams p = {};
+  if (d > 512) {
+    // row does not fit one accumulator: plain GEMM into emb_f32, then a row-normalise pass
+    p.n_tile = 512;
+    p.k_per_split = (f + 31) & ~31;
+    p.n_splits = 1;
+    p.c = emb_f32;
+    p.ldc = d;
+    int rc2 = launch_gemm_kmajor(feat, wt, n, d, f, p, stream);
+    if (rc2) return rc2;
+    normalize_fwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(emb_f32, (__nv_bfloat16*)emb_bf16,
+                                                          (__half*)emb_f16, inv_norm, n, d);
+    VLP_COUNT_LAUNCH(1);
+    VLP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   p.n_tile = (d + 15) & ~15;
   p.k_per_split = (f + 31) & ~31;
   p.n_splits = 1;
