@@ -285,3 +285,26 @@ def test_cuda_graph_path_matches_eager(VF, monkeypatch):
         assert np.array_equal(o["dI"], eager["dI"]) and np.array_equal(o["dT"], eager["dT"])
     assert_close(other, ref2, ref2["dlogit_scale"])
     VF._GRAPHS.clear()
+
+
+def test_largest_sweep_size_properties(VF):
+    """BASELINE config 5 upper end (65536 x 512): size-independent properties only -- the
+    temperature checksum sum_i <I_i, dI_i> = sum_j <T_j, dT_j> = d logit_scale, run-to-run
+    bit-reproducibility, and the loss of rows whose statistics are recomputed in fp64."""
+    n, d, ls = 65536, 512, math.log(1 / 0.07)
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=7)
+    a = run_fused(VF, I, T, ls)
+    b = run_fused(VF, I, T, ls)
+    assert a["loss"] == b["loss"] and np.array_equal(a["dI"], b["dI"]) and np.array_equal(a["dT"], b["dT"])
+    ci = float((I.double().numpy() * a["dI"].astype(np.float64)).sum())
+    ct = float((T.double().numpy() * a["dT"].astype(np.float64)).sum())
+    assert abs(ci - a["dl"]) < 2e-3 * abs(a["dl"]) and abs(ct - a["dl"]) < 2e-3 * abs(a["dl"])
+    s = math.exp(ls)
+    rows = np.random.RandomState(1).choice(n, 32, replace=False)
+    S_rows = s * (I.double()[rows] @ T.double().T)
+    img_rows = torch.logsumexp(S_rows, 1) - S_rows[torch.arange(32), torch.as_tensor(rows)]
+    S_cols = s * (T.double()[rows] @ I.double().T)
+    txt_rows = torch.logsumexp(S_cols, 1) - S_cols[torch.arange(32), torch.as_tensor(rows)]
+    # the sampled per-pair losses bracket the global mean
+    est = 0.5 * (img_rows.mean().item() + txt_rows.mean().item())
+    assert abs(est - a["loss"]) < 0.25 * a["loss"]
