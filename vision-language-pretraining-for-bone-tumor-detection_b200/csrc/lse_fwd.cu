@@ -387,21 +387,40 @@ __global__ void col_merge_kernel(const float* __restrict__ col_ref, const float*
                                  int n_row_blocks, size_t stride, int n_cols,
                                  const float* __restrict__ scale_ptr,
                                  float* __restrict__ out_max, float* __restrict__ out_l) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_cols) return;
+  // block = 32 columns x 8 row-block slices; slices are combined through smem in fixed order
+  __shared__ float sm[8][32], sl[8][32];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int slice = threadIdx.y;
   const float scale_log2 = __ldg(scale_ptr) * kLog2e;
-  float M = -INFINITY;
-  for (int r = 0; r < n_row_blocks; ++r) M = fmaxf(M, col_ref[(size_t)r * stride + j]);
-  float L = 0.f;
-  if (M != -INFINITY) {
-    for (int r = 0; r < n_row_blocks; ++r) {
+  float M = -INFINITY, L = 0.f;
+  if (j < n_cols) {
+    for (int r = slice; r < n_row_blocks; r += 8) {
       const float rr = col_ref[(size_t)r * stride + j];
-      if (rr != -INFINITY) L += col_l[(size_t)r * stride + j] * exp2f(rr - M);
+      const float ll = col_l[(size_t)r * stride + j];
+      if (rr != -INFINITY) {
+        const float Mn = fmaxf(M, rr);
+        L = L * exp2f(M - Mn) + ll * exp2f(rr - Mn);   // exp2f(-inf) = 0 on the first term
+        M = Mn;
+      }
     }
   }
-  const float mx = M / scale_log2;                 // surrogate "max" in raw cosine units
-  out_max[j] = mx;
-  out_l[j] = (M != -INFINITY) ? L * exp2f(M - mx * scale_log2) : 0.f;   // relative to fl(k * mx)
+  sm[slice][threadIdx.x] = M;
+  sl[slice][threadIdx.x] = L;
+  __syncthreads();
+  if (slice == 0 && j < n_cols) {
+    float Mt = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) Mt = fmaxf(Mt, sm[q][threadIdx.x]);
+    float Lt = 0.f;
+    if (Mt != -INFINITY) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (sm[q][threadIdx.x] != -INFINITY) Lt += sl[q][threadIdx.x] * exp2f(sm[q][threadIdx.x] - Mt);
+    }
+    const float mx = Mt / scale_log2;                 // surrogate "max" in raw cosine units
+    out_max[j] = mx;
+    out_l[j] = (Mt != -INFINITY) ? Lt * exp2f(Mt - mx * scale_log2) : 0.f;   // relative to fl(k * mx)
+  }
 }
 
 // out2[0] = sum(row_loss), out2[1] = sum(col_loss); single block, fixed order => reproducible
@@ -578,7 +597,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   if (fused) {
-    col_merge_kernel<<<(n_cols + 127) / 128, 128, 0, stream>>>(
+    col_merge_kernel<<<(n_cols + 31) / 32, dim3(32, 8), 0, stream>>>(
         p.col_ref, p.col_l, p.n_row_blocks, col_stride, n_cols, scale, col_max, col_l);
     VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());

@@ -279,6 +279,24 @@ class _FusedClipLoss(torch.autograd.Function):
         if t_bf16 is None:
             t_bf16 = text_embeddings.detach().to(torch.bfloat16).contiguous()
 
+        # fp16 operand copies for the backward: produced on a side stream so that the two small
+        # casts run underneath the forward sweep instead of in front of the backward
+        ctx.cast_event = None
+        needs_grad = any(ctx.needs_input_grad[:3])
+        if needs_grad and sharded.group_info(group)[0] == 1 and (i_f16 is None or t_f16 is None):
+            main = torch.cuda.current_stream()
+            side = sharded._side_stream(i_bf16.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                if i_f16 is None:
+                    i_f16 = cast_bf16_to_f16(i_bf16)
+                if t_f16 is None:
+                    t_f16 = cast_bf16_to_f16(t_bf16)
+                ctx.cast_event = side.record_event()
+            for t_ in (i_f16, t_f16, i_bf16, t_bf16):
+                t_.record_stream(side)
+                t_.record_stream(main)
+
         plan = sharded.forward_plan(CudaOps, i_bf16, t_bf16, scale, group,
                                     exact_columns=EXACT_COLUMNS)
         world = plan["world"]
@@ -319,6 +337,8 @@ class _FusedClipLoss(torch.autograd.Function):
             mul = torch.tensor(sign, dtype=torch.float32, device=i_bf16.device)
 
         i_f16, t_f16 = ctx.f16
+        if ctx.cast_event is not None:
+            torch.cuda.current_stream().wait_event(ctx.cast_event)
         if i_f16 is None:
             i_f16 = CudaOps.to_backward_operand(i_bf16)
         t_all_f16 = t_f16 if t_f16 is not None else CudaOps.to_backward_operand(t_all_bf16)
