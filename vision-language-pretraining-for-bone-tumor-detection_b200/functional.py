@@ -403,6 +403,7 @@ class _GraphEntry:
         self.graph = None
         self.out = None
         self.calls = 0
+        self.generation = 0      # bumped by every forward: guards the shared gradient buffers
 
     def capture(self):
         lib = _lib.load()
@@ -461,11 +462,12 @@ class _FusedClipLossGraphed(torch.autograd.Function):
             losses, d_i, d_t, d_ls = entry.out
         else:
             losses, d_i, d_t, d_ls = _fwd_bwd_eager(entry.i, entry.t, entry.ls, group, *needs)
-        # the graph's outputs are overwritten by the next replay: hand autograd private copies
+        # the graph's outputs are overwritten by the next replay: the three losses are copied out
+        # here; the gradients stay in place and backward checks that no other forward ran in between
         losses = losses.clone()
-        ctx.grads = (d_i.clone() if d_i is not None else None,
-                     d_t.clone() if d_t is not None else None,
-                     d_ls.clone() if d_ls is not None else None)
+        entry.generation += 1
+        ctx.entry, ctx.generation = entry, entry.generation
+        ctx.grads = (d_i, d_t, d_ls)
         ctx.grad_scale = float(grad_scale)
         ctx.in_dtypes = (image_embeddings.dtype, text_embeddings.dtype, logit_scale.dtype)
         ctx.ls_shape = logit_scale.shape
@@ -479,6 +481,11 @@ class _FusedClipLossGraphed(torch.autograd.Function):
                 "(VLP_B200_CUDA_GRAPH=0): the graph computes the gradients of `loss`")
         if g_loss is None:
             return (None,) * 5
+        if ctx.entry.generation != ctx.generation:
+            raise RuntimeError(
+                "fused CLIP loss (CUDA-graph mode): another forward of the same shape ran before this "
+                "backward and overwrote the gradient buffers; set VLP_B200_CUDA_GRAPH=0 for such "
+                "schedules")
         g = g_loss.detach().float() * ctx.grad_scale
         d_i, d_t, d_ls = ctx.grads
         out = [None, None, None, None, None]
