@@ -18,7 +18,7 @@ ls = torch.tensor([math.log(1/0.07)], device=dev, requires_grad=True)
 def step():
     Ii = I.detach().requires_grad_(True); Ti = T.detach().requires_grad_(True); ls.grad = None
     loss, _, _ = VF.fused_clip_loss_from_embeddings(Ii, Ti, ls, group=group); loss.backward()
-for _ in range(5): step()
+for _ in range(6): step()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
@@ -33,6 +33,8 @@ if rank == 0:
     lo = starts[1]; hi = starts[2] if len(starts) > 2 else len(evs)
     base = evs[lo].time_range.start
     for e in evs[lo:hi]:
-        print(f"{(e.time_range.start-base):9.1f} us  +{e.time_range.elapsed_us():8.1f}  {e.name[:70]}")
+        if e.name.startswith("nccl:"): continue
+        print(f"{(e.time_range.start-base):9.1f} us  +{e.time_range.elapsed_us():8.1f}  {e.name[:60]}")
     print("step span us:", evs[hi-1].time_range.end - base if hi-1 < len(evs) else None)
+VF.release_graphs()
 if world > 1: dist.destroy_process_group()

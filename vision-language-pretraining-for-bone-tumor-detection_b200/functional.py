@@ -421,7 +421,12 @@ def release_graphs() -> None:
     if _GRAPHS:
         if torch.cuda.is_available():
             torch.cuda.synchronize()
+        for entry in _GRAPHS.values():      # autograd contexts may still reference the entry
+            entry.graph = None
+            entry.out = None
         _GRAPHS.clear()
+        import gc
+        gc.collect()
 
 
 import atexit as _atexit  # noqa: E402

@@ -7,7 +7,7 @@ CPU test-suite on a numpy restatement of the kernel contracts under the ``gloo``
 (``tests/test_distributed_cpu.py``).  Only the per-rank tile work differs; the exchange steps are:
 
 forward   all_gather(T_loc)                       -> T_all            (b*D bf16 per rank)
-          all_gather(col (max, l) partials, diag) -> column statistics (3 * N fp32 per rank)
+          all_gather([col ref | col l | own diag])  -> column statistics ((2N + b) fp32 per rank)
           all_reduce([sum row_loss, sum col_loss])                     (2 fp32)
 backward  reduce_scatter(dT_all partial)          -> dT_loc           (N*D fp32 per rank)
           all_reduce(dscale)                                           (1 fp32)
@@ -75,9 +75,13 @@ def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: boo
         c_diag_own = c_diag_full[lo:lo + n_loc]
     r_max, r_lg, r_q, r_loss = ops.merge_stats(r_max_p, r_l_p, r_diag, scale)
     if world > 1:
-        c_max_p = all_gather_rows(c_max_p.unsqueeze(0), group, world)
-        c_l_p = all_gather_rows(c_l_p.unsqueeze(0), group, world)
-        c_diag = all_gather_rows(c_diag_own, group, world)
+        # one all-gather for the three small messages: [col ref (N) | col l (N) | own diag (b)]
+        n_all = c_max_p.shape[0]
+        packed = torch.cat([c_max_p, c_l_p, c_diag_own.to(c_max_p.dtype)]).unsqueeze(0)
+        gathered = all_gather_rows(packed, group, world)            # [world, 2N + b]
+        c_max_p = gathered[:, :n_all].contiguous()
+        c_l_p = gathered[:, n_all:2 * n_all].contiguous()
+        c_diag = gathered[:, 2 * n_all:].reshape(-1).contiguous()
     else:
         c_diag = c_diag_own
     c_max, c_lg, c_q, c_loss = ops.merge_stats(c_max_p, c_l_p, c_diag, scale)
