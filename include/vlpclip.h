@@ -10,7 +10,8 @@
  * The reference has no FFI of its own (pure Python over torch ops); the Python host side binds
  * these symbols with ctypes. Conventions:
  *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocator); the library
- *     never allocates persistent device memory and never frees;
+ *     never allocates persistent device memory and never frees -- the one exception is the peer
+ *     window of the sharded backward (vlpclip_peer_*), which must be exportable over CUDA IPC;
  *   - `stream` is a cudaStream_t passed as void*;
  *   - return value 0 = ok, negative = error; vlpclip_last_error() returns a thread-local message;
  *   - the N x N logit matrix is never written to global memory by any entry point.
@@ -116,6 +117,38 @@ int vlpclip_grad(const void* x_f16, int ldx, const void* y_f16, int ldy, const f
                  const float* y_q, int n_rows, int n_cols, int d, const float* scale, int diag_shift,
                  int n_global, float w_row, float w_col, const float* out_mul, int dx_bf16, void* dx,
                  float* dscale, void* workspace, size_t workspace_bytes, void* stream);
+
+/* host-only: the backward's work partition for n_clusters SM pairs (see grad_bwd.cu, "stream-K").
+ * seg rows = {cluster, row block, t0, t1, slot} (slot -1: whole row block, final rows written by the
+ * kernel; 0 / 1: partial block of that cluster), red rows = {row block, cluster, slot} in the
+ * order the pieces of split row blocks are summed.  Used by the CPU test-suite. */
+int vlpclip_grad_plan(int n_row_blocks, int tiles, int n_clusters, int* seg, int max_seg, int* n_seg,
+                      int* red, int max_red, int* n_red);
+
+/* ---- sharded backward: dX rows go straight to the rank that owns them (fused reduce-scatter) ----
+ * Same computation as vlpclip_grad, but final row r is stored (fp32, no out_mul) at
+ *   owner_rows[r / rows_per_owner] + (r % rows_per_owner) * d
+ * where owner_rows[o] points into rank o's peer window (NVLink peer memory, mapped with
+ * vlpclip_peer_open) at the slot reserved for the calling rank; the stores leave the SM from the
+ * accumulator epilogue, so the transfer overlaps the remaining tiles. After a cross-rank barrier
+ * every rank sums the slots of its own window in slot order with vlpclip_slot_sum (deterministic).
+ * Replaces reduce_scatter(dT_all) of the global-batch loss; owner_rows is a
+ * HOST array of n_owners (<= 8) device pointers.
+ */
+int vlpclip_grad_scatter(const void* x_f16, int ldx, const void* y_f16, int ldy, const float* x_max,
+                         const float* x_lg2l, const float* x_q, const float* y_max,
+                         const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
+                         const float* scale, int diag_shift, int n_global, float w_row, float w_col,
+                         void* const* owner_rows, int n_owners, int rows_per_owner, float* dscale,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* out[slot_elems] (fp32 or bf16) = out_mul * sum_s slots[s * slot_elems + .], s ascending */
+int vlpclip_slot_sum(const float* slots, int n_slots, size_t slot_elems, const float* out_mul,
+                     int out_bf16, void* out, void* stream);
+/* peer windows: cudaMalloc + CUDA IPC export / import (handle64 = 64-byte cudaIpcMemHandle_t) */
+int vlpclip_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int vlpclip_peer_open(const unsigned char* handle64, void** dev_ptr);
+int vlpclip_peer_close(void* dev_ptr);
+int vlpclip_peer_free(void* dev_ptr);
 
 /* ---- prologue: emb = normalize(feat @ W) (VisionLanguageModule.py:448-453) ----
  * feat [n, f] fp32, W [f, d] fp32 (x @ W convention, not nn.Linear).

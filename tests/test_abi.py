@@ -65,3 +65,47 @@ def test_kernels_are_blackwell_native():
     assert "UTMALDG" in sass       # cp.async.bulk.tensor
     assert "UBLKCP" in sass        # cp.async.bulk (DSMEM tile push)
     assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+# ---- backward work partition (host-side view of the kernel's "stream-K" split) ---------------
+def _grad_plan(n_row_blocks, tiles, n_clusters):
+    import ctypes
+
+    import numpy as np
+    lib = _lib.load()
+    cap = n_row_blocks * tiles + 4 * n_clusters
+    seg = np.zeros((cap, 5), np.int32)
+    red = np.zeros((cap, 3), np.int32)
+    ns, nr = ctypes.c_int(), ctypes.c_int()
+    rc = lib.vlpclip_grad_plan(n_row_blocks, tiles, n_clusters, seg.ctypes.data, cap,
+                               ctypes.byref(ns), red.ctypes.data, cap, ctypes.byref(nr))
+    assert rc == 0, lib.vlpclip_last_error()
+    return seg[:ns.value], red[:nr.value]
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 74), (2, 2, 74), (1, 1, 1), (32, 256, 72),
+                                   (256, 32, 72), (3, 5, 4), (512, 512, 74), (7, 1, 3),
+                                   (1, 300, 74), (128, 256, 72), (5, 7, 74)])
+def test_backward_work_partition_is_exact_and_balanced(shape):
+    """Every (row block, column tile) is swept exactly once, the load differs by <= 1 tile between
+    SM pairs, each pair owns at most one head and one tail partial block, and the pieces the
+    reduce kernel sums for a split row block are exactly the partial segments the sweep wrote."""
+    import numpy as np
+    r, c, p = shape
+    seg, red = _grad_plan(r, c, p)
+    cover = np.zeros((r, c), int)
+    load = {}
+    for cl, rb, t0, t1, slot in seg:
+        assert 0 <= t0 < t1 <= c
+        cover[rb, t0:t1] += 1
+        load[cl] = load.get(cl, 0) + (t1 - t0)
+        assert (slot == -1) == (t0 == 0 and t1 == c)
+    assert (cover == 1).all()
+    assert max(load.values()) - min(load.values()) <= 1
+    partial = [(rb, cl, slot) for cl, rb, t0, t1, slot in seg if slot >= 0]
+    assert len({(cl, slot) for _, cl, slot in partial}) == len(partial)     # slots never reused
+    assert sorted(partial) == sorted(map(tuple, red.tolist()))
+    # summation order inside a row block = ascending cluster index (fixed => reproducible)
+    for rb in set(red[:, 0].tolist()):
+        cls = red[red[:, 0] == rb][:, 1]
+        assert (np.diff(cls) > 0).all()

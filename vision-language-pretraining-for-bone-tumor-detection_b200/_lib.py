@@ -35,6 +35,17 @@ _SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                              c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                              c_size_t, c_void_p]),
+    "vlpclip_grad_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                  c_void_p]),
+    "vlpclip_grad_scatter": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                     c_int, c_int, c_float, c_float, c_void_p, c_int, c_int,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlpclip_slot_sum": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
+    "vlpclip_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
+    "vlpclip_peer_open": (c_int, [c_void_p, c_void_p]),
+    "vlpclip_peer_close": (c_int, [c_void_p]),
+    "vlpclip_peer_free": (c_int, [c_void_p]),
     "vlpclip_project_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlpclip_project_normalize_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

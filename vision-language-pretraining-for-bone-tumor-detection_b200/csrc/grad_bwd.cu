@@ -39,6 +39,12 @@ constexpr uint32_t BWD_TMEM_X = 0;          // producer: X block (fp16 packed), 
 // producer S buffers (128 columns each) at the top of TMEM: two while d <= 512, one for d <= 768
 constexpr float G_SCALE = 8192.f;           // 2^13: keeps softmax tails out of fp16 subnormals
 
+constexpr int MAX_OWNERS = 8;   // one NVSwitch box
+struct RowScatter {
+  void* base[MAX_OWNERS];
+  int rows_per_owner;   // 0: disabled
+};
+
 struct GradParams {
   const __half* x;
   int ldx;
@@ -53,18 +59,96 @@ struct GradParams {
   const float* yq;      // [n_cols] 1 - P_col(positive)
   float w_row, w_col;
   int n_rows, n_cols, d;
-  int kblocks, total_tiles, tiles_per_chunk, n_chunks, n_row_blocks;
+  int kblocks, total_tiles, n_row_blocks;
   int db0, ndb;         // consumer: first 64-column block / number of blocks of dX in this pass
   int diag_shift;
   const float* scale_ptr;  // device scalar s
   float out_scale;      // 1 / (2 n_global) / 2^13   (multiplied by s in the epilogue)
-  void* dx;             // [n_rows, d] final output (n_chunks == 1; fp32 or bf16) or fp32 per-chunk
-                        // partials [n_chunks][n_rows, d]
-  int dx_bf16;          // final output dtype when written by this kernel
+  void* dx;             // [n_rows, d] final output (fp32 or bf16): row blocks swept by ONE cluster
+  int dx_bf16;          // final output dtype
   const float* out_mul; // optional device scalar multiplied into the output (upstream gradient)
-  size_t chunk_stride;  // elements between the partial buffers of consecutive chunks
-  float* ds_part;       // [n_items * 8] or nullptr
+  float* part;          // [n_clusters][2][128, d] fp32 partial blocks of row blocks that are split
+                        // between clusters (slot 0: head segment, slot 1: tail segment)
+  float* ds_part;       // [n_clusters * 8] or nullptr
+  RowScatter scatter;   // optional: final rows go to per-owner buffers (fused reduce-scatter)
 };
+
+// ---- work partition ------------------------------------------------------------------------
+// The (row block, column tile) grid is flattened row-block-major and cut into n_clusters equal
+// contiguous ranges ("stream-K"): every cluster sweeps the same number of tiles (+-1) whatever the
+// shape.  A range crosses row-block boundaries, so a cluster works through SEGMENTS
+// (rb, [t0, t1)); a segment covering its whole row block writes the final rows, the (at most two)
+// partial ones per cluster go to that cluster's partial slots and dx_reduce_kernel sums the
+// pieces of each split row block in cluster order (fixed order => bit-reproducible).
+struct Segment {
+  int rb, t0, t1;
+  int slot;   // -1: whole row block; 0 / 1: partial (head / tail segment of the cluster's range)
+};
+__host__ __device__ inline long long range_begin(int cluster, int n_clusters, long long total) {
+  return total * cluster / n_clusters;
+}
+struct WorkRange {
+  long long start, end, cur;
+  int tiles;
+  __host__ __device__ WorkRange(int cluster, int n_clusters, int n_row_blocks, int total_tiles) {
+    const long long total = (long long)n_row_blocks * total_tiles;
+    start = range_begin(cluster, n_clusters, total);
+    end = range_begin(cluster + 1, n_clusters, total);
+    cur = start;
+    tiles = total_tiles;
+  }
+  __host__ __device__ bool next(Segment& s) {
+    if (cur >= end) return false;
+    s.rb = (int)(cur / tiles);
+    const long long rb0 = (long long)s.rb * tiles;
+    const long long seg_end = end < rb0 + tiles ? end : rb0 + tiles;
+    s.t0 = (int)(cur - rb0);
+    s.t1 = (int)(seg_end - rb0);
+    s.slot = (s.t0 == 0 && s.t1 == tiles) ? -1 : (cur == start ? 0 : 1);
+    cur = seg_end;
+    return true;
+  }
+};
+// cluster whose range holds flattened tile x
+__host__ __device__ inline int range_owner(long long x, int n_clusters, long long total) {
+  int c = (int)((x * n_clusters) / total);
+  if (c >= n_clusters) c = n_clusters - 1;
+  while (c + 1 < n_clusters && range_begin(c + 1, n_clusters, total) <= x) ++c;
+  while (c > 0 && range_begin(c, n_clusters, total) > x) --c;
+  return c;
+}
+
+// pieces of a split row block, as dx_reduce_kernel sums them
+struct SplitBlock {
+  int c_first, c_last, first_slot;
+};
+__host__ __device__ inline bool split_block(int rb, int tiles, int n_clusters, long long total,
+                                            SplitBlock& sb) {
+  const long long x0 = (long long)rb * tiles, x1 = x0 + tiles - 1;
+  sb.c_first = range_owner(x0, n_clusters, total);
+  sb.c_last = range_owner(x1, n_clusters, total);
+  sb.first_slot = range_begin(sb.c_first, n_clusters, total) == x0 ? 0 : 1;
+  return sb.c_first != sb.c_last;
+}
+__host__ __device__ inline bool split_source(const SplitBlock& sb, int c, int n_clusters,
+                                             long long total, int& slot) {
+  if (range_begin(c, n_clusters, total) == range_begin(c + 1, n_clusters, total)) return false;
+  slot = c == sb.c_first ? sb.first_slot : 0;
+  return true;
+}
+
+// destination of final row `row`: plain [n_rows, d] or, for the fused reduce-scatter, the buffer of
+// the rank that owns the row (peer memory over NVLink), at the row's index inside that shard
+__device__ __forceinline__ size_t scatter_row(const RowScatter& sc, int row, uint8_t*& base,
+                                              void* dx) {
+  if (sc.rows_per_owner <= 0) {
+    base = reinterpret_cast<uint8_t*>(dx);
+    return (size_t)row;
+  }
+  const int o = row / sc.rows_per_owner;
+  base = reinterpret_cast<uint8_t*>(sc.base[o]);
+  return (size_t)(row - o * sc.rows_per_owner);
+}
 
 struct BwdBarriers {
   uint64_t full[P_STAGES];
@@ -192,7 +276,6 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const int n_items = p.n_row_blocks * p.n_chunks;
   const float scale_dev = __ldg(p.scale_ptr);
   const float scale_log2 = scale_dev * kLog2e;
   const uint32_t nbuf = p.kblocks <= 8 ? 2u : 1u;
@@ -204,10 +287,10 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     // =====================================================================================
     if (warp == 0) {
       uint32_t it = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters) {
-        const int chunk = item / p.n_row_blocks;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      WorkRange work(cluster_id, n_clusters, p.n_row_blocks, p.total_tiles);
+      Segment sg;
+      while (work.next(sg)) {
+        const int t0 = sg.t0, t1 = sg.t1;
         for (int t = t0; t < t1; ++t)
           for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
             const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
@@ -225,10 +308,10 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     } else if (warp == 1) {
       const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_K, 128, 128);
       uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
-        const int chunk = item / p.n_row_blocks;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      WorkRange work(cluster_id, n_clusters, p.n_row_blocks, p.total_tiles);
+      Segment sg;
+      for (; work.next(sg); ++item_ctr) {
+        const int t0 = sg.t0, t1 = sg.t1;
         mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
         tc_fence_after();
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
@@ -270,11 +353,12 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
       const int dp = p.kblocks * 64;
       const uint32_t sw = row_in_blk & 7;
       uint32_t tile_ctr = 0, item_ctr = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
-        const int chunk = item / p.n_row_blocks;
-        const int rb = item % p.n_row_blocks;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      double ds_total = 0.0;   // lane 0: this warp's share of dscale over the cluster's whole range
+      WorkRange work(cluster_id, n_clusters, p.n_row_blocks, p.total_tiles);
+      Segment sg;
+      for (; work.next(sg); ++item_ctr) {
+        const int rb = sg.rb;
+        const int t0 = sg.t0, t1 = sg.t1;
         const int row = rb * 128 + row_in_blk;
         const bool row_ok = row < p.n_rows;
         if (item_ctr > 0) {
@@ -384,12 +468,12 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
                 : "memory");
           }
         }
-        if (p.ds_part != nullptr) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) ds_acc += __shfl_xor_sync(0xffffffffu, ds_acc, o);
-          if (lane == 0) p.ds_part[(size_t)item * 8 + (warp - 2)] = ds_acc;
-        }
+        for (int o = 16; o > 0; o >>= 1) ds_acc += __shfl_xor_sync(0xffffffffu, ds_acc, o);
+        ds_total += (double)ds_acc;
       }
+      if (p.ds_part != nullptr && lane == 0)
+        p.ds_part[(size_t)cluster_id * 8 + (warp - 2)] = (float)ds_total;
       // drain: the consumer must have released every slot we pushed before we may exit
       for (uint32_t back = 0; back < 2 && back < tile_ctr; ++back) {
         const uint32_t tc = tile_ctr - 1 - back;
@@ -403,10 +487,10 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     const int n_nc = (p.ndb + 3) / 4;  // 256-wide accumulator chunks of this pass
     if (warp == 0) {
       uint32_t it = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters) {
-        const int chunk = item / p.n_row_blocks;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      WorkRange work(cluster_id, n_clusters, p.n_row_blocks, p.total_tiles);
+      Segment sg;
+      while (work.next(sg)) {
+        const int t0 = sg.t0, t1 = sg.t1;
         for (int t = t0; t < t1; ++t)
           for (int nc = 0; nc < n_nc; ++nc) {
             const int nb = min(4, p.ndb - nc * 4);
@@ -426,10 +510,10 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
       }
     } else if (warp == 1) {
       uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
-        const int chunk = item / p.n_row_blocks;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      WorkRange work(cluster_id, n_clusters, p.n_row_blocks, p.total_tiles);
+      Segment sg;
+      for (; work.next(sg); ++item_ctr) {
+        const int t0 = sg.t0, t1 = sg.t1;
         if (item_ctr > 0) {
           mbar_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1);
           tc_fence_after();
@@ -472,18 +556,26 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
       const uint32_t row_in_blk = quarter * 32 + lane;
       const uint32_t lane_addr = (quarter * 32u) << 16;
       uint32_t item_ctr = 0;
-      for (int item = cluster_id; item < n_items; item += n_clusters, ++item_ctr) {
-        const int rb = item % p.n_row_blocks;
-        const int row = rb * 128 + row_in_blk;
+      WorkRange work(cluster_id, n_clusters, p.n_row_blocks, p.total_tiles);
+      Segment sg;
+      for (; work.next(sg); ++item_ctr) {
+        const int row = sg.rb * 128 + row_in_blk;
         mbar_wait(smem_u32(&bars->acc_full), item_ctr & 1);
         tc_fence_after();
-        const int chunk = item / p.n_row_blocks;
-        const bool final_out = p.n_chunks == 1;
+        const bool final_out = sg.slot < 0;
         const float mulv =
             scale_dev * ((final_out && p.out_mul) ? p.out_scale * __ldg(p.out_mul) : p.out_scale);
-        const size_t roff = (size_t)chunk * p.chunk_stride + (size_t)(row < p.n_rows ? row : 0) * p.d;
-        float* orow = reinterpret_cast<float*>(p.dx) + roff;
-        __nv_bfloat16* orow_b = reinterpret_cast<__nv_bfloat16*>(p.dx) + roff;
+        float* orow;
+        __nv_bfloat16* orow_b;
+        if (final_out) {
+          uint8_t* base;
+          const size_t r = scatter_row(p.scatter, row < p.n_rows ? row : 0, base, p.dx);
+          orow = reinterpret_cast<float*>(base) + r * p.d;
+          orow_b = reinterpret_cast<__nv_bfloat16*>(base) + r * p.d;
+        } else {
+          orow = p.part + ((size_t)(cluster_id * 2 + sg.slot) * 128 + row_in_blk) * p.d;
+          orow_b = nullptr;
+        }
         const int cbase = p.db0 * 64;   // first dX column of this pass
         for (int cc = 0; cc < p.ndb * 64; cc += 32) {
           uint32_t v[32];
@@ -613,31 +705,45 @@ __global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __re
   }
 }
 
-// dx = mul * sum over chunks of the per-chunk partial blocks, fixed order (bit reproducible)
-__global__ void dx_reduce_kernel(const float4* __restrict__ part, size_t chunk_stride4, int n_chunks,
-                                 size_t n4, const float* __restrict__ out_mul, int out_bf16,
-                                 void* __restrict__ dx) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+// Row blocks whose column sweep was split between clusters: dx rows = mul * (sum of the partial
+// blocks in cluster order).  One block row of the grid per row block; unsplit ones return at once.
+constexpr int RED_SPLIT = 8;
+__global__ void dx_reduce_kernel(const float* __restrict__ part, int n_clusters, int n_row_blocks,
+                                 int tiles, int n_rows, int d, const float* __restrict__ out_mul,
+                                 int out_bf16, void* __restrict__ dx, const RowScatter scatter) {
+  const int rb = blockIdx.x;
+  const long long total = (long long)n_row_blocks * tiles;
+  SplitBlock sb;
+  if (!split_block(rb, tiles, n_clusters, total, sb)) return;
+  const int rows = min(128, n_rows - rb * 128);
+  const int d4 = d >> 2;
   const float m = out_mul ? __ldg(out_mul) : 1.f;
-  for (; i < n4; i += stride) {
-    float4 a = part[i];
-    for (int c = 1; c < n_chunks; ++c) {
-      const float4 b = part[(size_t)c * chunk_stride4 + i];
+  const size_t blk4 = (size_t)128 * d4;
+  const float4* part4 = reinterpret_cast<const float4*>(part);
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < rows * d4; i += gridDim.y * blockDim.x) {
+    const int r = i / d4, c4 = i - r * d4;
+    const size_t off = (size_t)r * d4 + c4;
+    float4 a = part4[(size_t)(sb.c_first * 2 + sb.first_slot) * blk4 + off];
+    for (int c = sb.c_first + 1; c <= sb.c_last; ++c) {
+      int slot;
+      if (!split_source(sb, c, n_clusters, total, slot)) continue;
+      const float4 b = part4[(size_t)(c * 2 + slot) * blk4 + off];
       a.x += b.x;
       a.y += b.y;
       a.z += b.z;
       a.w += b.w;
     }
+    uint8_t* base;
+    const size_t orow = scatter_row(scatter, rb * 128 + r, base, dx);
     if (out_bf16) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(a.x * m, a.y * m);
       __nv_bfloat162 hi = __floats2bfloat162_rn(a.z * m, a.w * m);
       uint2 o;
       o.x = *reinterpret_cast<uint32_t*>(&lo);
       o.y = *reinterpret_cast<uint32_t*>(&hi);
-      reinterpret_cast<uint2*>(dx)[i] = o;
+      reinterpret_cast<uint2*>(base)[orow * d4 + c4] = o;
     } else {
-      reinterpret_cast<float4*>(dx)[i] = make_float4(a.x * m, a.y * m, a.z * m, a.w * m);
+      reinterpret_cast<float4*>(base)[orow * d4 + c4] = make_float4(a.x * m, a.y * m, a.z * m, a.w * m);
     }
   }
 }
@@ -656,28 +762,6 @@ __global__ void ds_reduce_kernel(const float* __restrict__ part, int n, float mu
   if (threadIdx.x == 0) out[0] = (float)(sh[0] * (double)mul);
 }
 
-static void pick_chunks_pairs(int n_row_blocks, int total_tiles, int n_pairs, int* n_chunks,
-                              int* tiles_per_chunk) {
-  int best_c = 1;
-  double best_eff = -1.0;
-  const int max_c = total_tiles < 16 ? total_tiles : 16;
-  for (int c = 1; c <= max_c; ++c) {
-    const int tpc = (total_tiles + c - 1) / c;
-    const int cc = (total_tiles + tpc - 1) / tpc;
-    if (cc != c) continue;
-    const long items = (long)n_row_blocks * cc;
-    const long waves = (items + n_pairs - 1) / n_pairs;
-    // per-item fixed cost (X staging + accumulator flush) ~ 3 tiles worth
-    double eff = (double)items * tpc / ((double)waves * n_pairs * (tpc + 3.0));
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best_c = cc;
-    }
-  }
-  *tiles_per_chunk = (total_tiles + best_c - 1) / best_c;
-  *n_chunks = (total_tiles + *tiles_per_chunk - 1) / *tiles_per_chunk;
-}
-
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 static int n_pairs_of_device() {
@@ -685,12 +769,17 @@ static int n_pairs_of_device() {
   return n > 1 ? n / 2 : 74;   // no device (host-side size queries): assume a B200
 }
 
+static int plan_clusters(int n_row_blocks, int total_tiles) {
+  const long long total = (long long)n_row_blocks * total_tiles;
+  const int n_pairs = n_pairs_of_device();
+  return total < n_pairs ? (int)total : n_pairs;
+}
+
 static size_t grad_ws_bytes(int n_rows, int n_cols, int d) {
   const size_t nrb = (n_rows + 127) / 128, nt = (n_cols + 127) / 128;
-  int n_chunks, tpc;
-  pick_chunks_pairs((int)nrb, (int)nt, n_pairs_of_device(), &n_chunks, &tpc);
-  const size_t partials = n_chunks > 1 ? align256((size_t)n_chunks * n_rows * d * 4) : 0;
-  return 3 * align256(nrb * 128 * 4) + 3 * align256(nt * 128 * 4) + align256(nrb * 16 * 8 * 4) +
+  const size_t max_pairs = 74;   // sized for a whole B200 whatever the current SM limit
+  const size_t partials = align256(max_pairs * 2 * 128 * (size_t)d * 4);
+  return 3 * align256(nrb * 128 * 4) + 3 * align256(nt * 128 * 4) + align256(max_pairs * 8 * 4) +
          partials + 1024;
 }
 
@@ -705,16 +794,16 @@ size_t vlpclip_grad_workspace_bytes(int n_rows, int n_cols, int d) {
   return grad_ws_bytes(n_rows, n_cols, d);
 }
 
-int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_max,
-                 const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
-                 const float* y_q, int n_rows,
-                 int n_cols, int d, const float* scale, int diag_shift, int n_global, float w_row,
-                 float w_col, const float* out_mul, int dx_bf16, void* dx, float* dscale,
-                 void* workspace, size_t workspace_bytes, void* stream_) {
+static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float* x_max,
+                     const float* x_lg2l, const float* x_q, const float* y_max,
+                     const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
+                     const float* scale, int diag_shift, int n_global, float w_row, float w_col,
+                     const float* out_mul, int dx_bf16, void* dx, float* dscale, void* workspace,
+                     size_t workspace_bytes, void* stream_, const RowScatter* scatter) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "grad: empty problem (%d x %d)", n_rows, n_cols);
-  if (!x || !y || !scale || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q || !dx ||
-      !workspace)
+  if (!x || !y || !scale || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q ||
+      (!dx && !scatter) || !workspace)
     return fail(-1, "grad: null pointer");
   if (d <= 0 || d % 8 != 0 || d > 768)
     return fail(-1, "grad: embedding dim %d unsupported (need a multiple of 8, <= 768)", d);
@@ -739,8 +828,8 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   p.kblocks = (d + 63) / 64;
   p.total_tiles = (n_cols + 127) / 128;
   p.n_row_blocks = (n_rows + 127) / 128;
-  const int n_pairs = n_pairs_of_device();
-  pick_chunks_pairs(p.n_row_blocks, p.total_tiles, n_pairs, &p.n_chunks, &p.tiles_per_chunk);
+  const int clusters = plan_clusters(p.n_row_blocks, p.total_tiles);
+  if (clusters > 74) return fail(-1, "grad: %d SM pairs exceed the workspace layout", clusters);
   p.diag_shift = diag_shift;
   p.w_row = w_row;
   p.w_col = w_col;
@@ -767,12 +856,13 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
   int* fast_flag = (int*)(ws + 256);
   ws += 512;
   float* ds_part = (float*)ws;
-  ws += align256((size_t)p.n_row_blocks * 16 * 8 * 4);
+  ws += align256((size_t)74 * 8 * 4);
   float* dx_part = (float*)ws;
-  p.dx = p.n_chunks > 1 ? (void*)dx_part : dx;
+  p.dx = dx;
+  p.part = dx_part;
   p.dx_bf16 = dx_bf16;
   p.out_mul = out_mul;
-  p.chunk_stride = (size_t)n_rows * d;
+  if (scatter) p.scatter = *scatter;
   p.xmax = xmax;
   p.xlg = xlg;
   p.ymax = ymax;
@@ -809,8 +899,6 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
                                      (int)smem));
     attr_set = true;
   }
-  const int n_items = p.n_row_blocks * p.n_chunks;
-  const int clusters = n_items < n_pairs ? n_items : n_pairs;
   // the dX block of a pass must fit the consumer's 512 TMEM columns: d <= 512 in one pass,
   // 512 < d <= 768 in two passes of half the 64-column blocks each (S is recomputed per pass)
   const int n_pass = p.kblocks > 8 ? 2 : 1;
@@ -823,21 +911,168 @@ int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_
     grad_pair_kernel<<<clusters * 2, BWD_THREADS, smem, stream>>>(map_k, map_mn, p);
     VLP_COUNT_LAUNCH(1);
   }
-  if (p.n_chunks > 1) {
-    const size_t n4 = (size_t)n_rows * d / 4;
-    int blocks = (int)((n4 + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    dx_reduce_kernel<<<blocks, 256, 0, stream>>>((const float4*)dx_part, n4, p.n_chunks, n4, out_mul,
-                                                 dx_bf16, dx);
+  {
+    // (a no-op for row blocks swept by a single cluster)
+    dx_reduce_kernel<<<dim3(p.n_row_blocks, RED_SPLIT), 256, 0, stream>>>(
+        dx_part, clusters, p.n_row_blocks, p.total_tiles, n_rows, d, out_mul, dx_bf16, dx, p.scatter);
     VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
   }
   if (dscale) {
-    ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, n_items * 8, 1.0f / (2.0f * (float)n_global),
+    ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, clusters * 8, 1.0f / (2.0f * (float)n_global),
                                             dscale);
   VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
   }
+  return 0;
+}
+
+// host-side view of the work partition (tests): seg rows = {cluster, row block, t0, t1, slot},
+// red rows = {row block, cluster, slot} in summation order
+int vlpclip_grad_plan(int n_row_blocks, int tiles, int n_clusters, int* seg, int max_seg, int* n_seg,
+                      int* red, int max_red, int* n_red) {
+  if (n_row_blocks <= 0 || tiles <= 0 || n_clusters <= 0 || !seg || !red || !n_seg || !n_red)
+    return fail(-1, "grad_plan: bad arguments");
+  const long long total = (long long)n_row_blocks * tiles;
+  int ns = 0, nr = 0;
+  for (int c = 0; c < n_clusters; ++c) {
+    WorkRange w(c, n_clusters, n_row_blocks, tiles);
+    Segment sg;
+    while (w.next(sg)) {
+      if (ns >= max_seg) return fail(-1, "grad_plan: segment buffer too small");
+      int* o = seg + 5 * ns++;
+      o[0] = c; o[1] = sg.rb; o[2] = sg.t0; o[3] = sg.t1; o[4] = sg.slot;
+    }
+  }
+  for (int rb = 0; rb < n_row_blocks; ++rb) {
+    SplitBlock sb;
+    if (!split_block(rb, tiles, n_clusters, total, sb)) continue;
+    for (int c = sb.c_first; c <= sb.c_last; ++c) {
+      int slot;
+      if (!split_source(sb, c, n_clusters, total, slot)) continue;
+      if (nr >= max_red) return fail(-1, "grad_plan: reduce buffer too small");
+      int* o = red + 3 * nr++;
+      o[0] = rb; o[1] = c; o[2] = slot;
+    }
+  }
+  *n_seg = ns;
+  *n_red = nr;
+  return 0;
+}
+
+int vlpclip_grad(const void* x, int ldx, const void* y, int ldy, const float* x_max,
+                 const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
+                 const float* y_q, int n_rows, int n_cols, int d, const float* scale,
+                 int diag_shift, int n_global, float w_row, float w_col, const float* out_mul,
+                 int dx_bf16, void* dx, float* dscale, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  return grad_impl(x, ldx, y, ldy, x_max, x_lg2l, x_q, y_max, y_lg2l, y_q, n_rows, n_cols, d, scale,
+                   diag_shift, n_global, w_row, w_col, out_mul, dx_bf16, dx, dscale, workspace,
+                   workspace_bytes, stream, nullptr);
+}
+
+int vlpclip_grad_scatter(const void* x, int ldx, const void* y, int ldy, const float* x_max,
+                         const float* x_lg2l, const float* x_q, const float* y_max,
+                         const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
+                         const float* scale, int diag_shift, int n_global, float w_row, float w_col,
+                         void* const* owner_rows, int n_owners, int rows_per_owner, float* dscale,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!owner_rows || n_owners <= 0 || n_owners > MAX_OWNERS)
+    return fail(-1, "grad_scatter: need 1..%d owner buffers (got %d)", MAX_OWNERS, n_owners);
+  if (rows_per_owner <= 0 || (long long)rows_per_owner * n_owners < n_rows)
+    return fail(-1, "grad_scatter: %d owners x %d rows do not cover %d rows", n_owners,
+                rows_per_owner, n_rows);
+  RowScatter sc = {};
+  for (int i = 0; i < n_owners; ++i) {
+    if (!owner_rows[i] || (reinterpret_cast<uintptr_t>(owner_rows[i]) & 15) != 0)
+      return fail(-1, "grad_scatter: owner buffer %d is null or not 16-byte aligned", i);
+    sc.base[i] = owner_rows[i];
+  }
+  sc.rows_per_owner = rows_per_owner;
+  return grad_impl(x, ldx, y, ldy, x_max, x_lg2l, x_q, y_max, y_lg2l, y_q, n_rows, n_cols, d, scale,
+                   diag_shift, n_global, w_row, w_col, nullptr, 0, nullptr, dscale, workspace,
+                   workspace_bytes, stream, &sc);
+}
+
+// out = mul * (slot 0 + slot 1 + ... ) in slot order: the local half of the fused reduce-scatter
+// (every peer has stored its partial rows into its slot of this rank's window)
+__global__ void slot_sum_kernel(const float4* __restrict__ slots, size_t slot_stride4, int n_slots,
+                                size_t n4, const float* __restrict__ out_mul, int out_bf16,
+                                void* __restrict__ out) {
+  const float m = out_mul ? __ldg(out_mul) : 1.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = slots[i];
+    for (int s = 1; s < n_slots; ++s) {
+      const float4 b = slots[(size_t)s * slot_stride4 + i];
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    if (out_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(a.x * m, a.y * m);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(a.z * m, a.w * m);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(out)[i] = o;
+    } else {
+      reinterpret_cast<float4*>(out)[i] = make_float4(a.x * m, a.y * m, a.z * m, a.w * m);
+    }
+  }
+}
+
+int vlpclip_slot_sum(const float* slots, int n_slots, size_t slot_elems, const float* out_mul,
+                     int out_bf16, void* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!slots || !out || n_slots <= 0 || slot_elems == 0 || slot_elems % 4 != 0)
+    return fail(-1, "slot_sum: bad arguments (n_slots %d, slot_elems %zu)", n_slots, slot_elems);
+  if ((reinterpret_cast<uintptr_t>(slots) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0)
+    return fail(-1, "slot_sum: buffers must be 16-byte aligned");
+  const size_t n4 = slot_elems / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  slot_sum_kernel<<<blocks, 256, 0, stream>>>((const float4*)slots, n4, n_slots, n4, out_mul,
+                                              out_bf16, out);
+  VLP_COUNT_LAUNCH(1);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- peer windows (CUDA IPC): the only device memory this library allocates itself ----------
+int vlpclip_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) return fail(-1, "peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  VLP_CUDA_OK(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(-2, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+  }
+  VLP_CUDA_OK(cudaMemset(p, 0, bytes));
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+
+int vlpclip_peer_open(const unsigned char* handle64, void** dev_ptr) {
+  if (!dev_ptr || !handle64) return fail(-1, "peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  VLP_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int vlpclip_peer_close(void* dev_ptr) {
+  if (dev_ptr) VLP_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  return 0;
+}
+
+int vlpclip_peer_free(void* dev_ptr) {
+  if (dev_ptr) VLP_CUDA_OK(cudaFree(dev_ptr));
   return 0;
 }
 

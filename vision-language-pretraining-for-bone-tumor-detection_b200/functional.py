@@ -211,8 +211,177 @@ def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_globa
     return dx, ds
 
 
+# ----------------------------------------------------------------------------------------------
+# fused reduce-scatter over NVLink peer memory
+# ----------------------------------------------------------------------------------------------
+# VLP_B200_PEER_RS=auto|1|0: the sharded backward stores dT rows from the accumulator epilogue
+# straight into the owning rank's window (CUDA IPC peer memory) instead of calling NCCL
+# reduce-scatter on a [N, D] fp32 partial.  auto = use it when every rank could map every window.
+PEER_RS_MODE = os.environ.get("VLP_B200_PEER_RS", "auto").lower()
+MAX_PEER_RANKS = 8
+_PEER_WINDOWS = {}
+
+
+class PeerWindow:
+    """fp32 window [2 parities][world slots][rows, d] on every rank, mapped into every peer.
+
+    Rank s writes its partial of the rows owned by rank o into slot s of o's window; after a
+    collective that all ranks pass, o sums its slots in slot order (``vlpclip_slot_sum``).  Two
+    parities alternate between calls so that a rank still summing call k is never overwritten
+    by a peer already storing call k+1."""
+
+    def __init__(self, group, world: int, rank: int, rows: int, d: int, device):
+        import ctypes
+        dist = sharded._dist()
+        lib = _lib.load()
+        self.group, self.world, self.rank = group, world, rank
+        self.rows, self.d = rows, d
+        self.slot_bytes = rows * d * 4
+        self.local = None
+        self.peers = [None] * world
+        self.parity = 0
+        ok = 1
+        handle = (ctypes.c_ubyte * 64)()
+        ptr = ctypes.c_void_p()
+        if lib.vlpclip_peer_alloc(2 * world * self.slot_bytes, ctypes.byref(ptr), handle) == 0:
+            self.local = ptr.value
+        else:
+            ok = 0
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle) if ok else None, group=group)
+        if ok and all(h is not None for h in handles):
+            for r, h in enumerate(handles):
+                if r == rank:
+                    self.peers[r] = self.local
+                    continue
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                q = ctypes.c_void_p()
+                if lib.vlpclip_peer_open(buf, ctypes.byref(q)) != 0:
+                    ok = 0
+                    break
+                self.peers[r] = q.value
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also a barrier
+        self.ok = bool(flag.item())
+        if not self.ok:
+            self.error = lib.vlpclip_last_error().decode(errors="replace")
+            self.close(barrier=False)
+
+    def next_parity(self) -> int:
+        self.parity ^= 1
+        return self.parity
+
+    def owner_rows(self, parity: int):
+        """Host array: for every owner o, the address of THIS rank's slot inside o's window."""
+        import ctypes
+        off = (parity * self.world + self.rank) * self.slot_bytes
+        return (ctypes.c_void_p * self.world)(*[p + off for p in self.peers])
+
+    def slots(self, parity: int) -> int:
+        return self.local + parity * self.world * self.slot_bytes
+
+    def close(self, barrier: bool = True):
+        lib = _lib.load()
+        for r, q in enumerate(self.peers):
+            if q is not None and r != self.rank:
+                lib.vlpclip_peer_close(q)
+        self.peers = [None] * self.world
+        if barrier:      # nobody may free a window a peer still has mapped
+            try:
+                sharded._dist().barrier(group=self.group)
+            except Exception:
+                barrier = False
+        if self.local is not None and barrier:
+            lib.vlpclip_peer_free(self.local)
+        self.local = None      # (without a barrier the memory is left to process exit)
+
+
+def peer_window(group, world: int, rank: int, rows: int, d: int, device) -> Optional[PeerWindow]:
+    """The window for this (group, shard shape), or None when peer mode is off / unavailable.
+    Collective: every rank of ``group`` must call it at the same point (first use of a shape)."""
+    if PEER_RS_MODE == "0" or world < 2 or world > MAX_PEER_RANKS or device.type != "cuda":
+        return None
+    if torch.cuda.is_current_stream_capturing():
+        w = _PEER_WINDOWS.get((id(group), rows, d, device.index))
+        return w if (w is not None and w.ok) else None
+    key = (id(group), rows, d, device.index)
+    w = _PEER_WINDOWS.get(key)
+    if w is None:
+        w = _PEER_WINDOWS[key] = PeerWindow(group, world, rank, rows, d, device)
+        if not w.ok:
+            msg = f"vlp_b200: NVLink peer windows unavailable ({w.error}); using NCCL reduce-scatter"
+            if PEER_RS_MODE == "1":
+                raise RuntimeError(msg)
+            if rank == 0:
+                import warnings
+                warnings.warn(msg)
+    return w if w.ok else None
+
+
+def release_peer_windows() -> None:
+    if _PEER_WINDOWS:
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        for w in _PEER_WINDOWS.values():
+            if w.ok and w.local is not None:
+                w.close(barrier=True)
+        _PEER_WINDOWS.clear()
+
+
+def _grad_scatter(x_f16, y_f16, x_stats, y_stats, scale, diag_shift: int, n_global: int,
+                  w_row: float, w_col: float, want_dscale: bool, window: PeerWindow):
+    """dX = grad(...) with row r stored into the window of rank r // window.rows (this rank's
+    slot).  Returns (parity, dscale); finish with ``_scatter_finish`` after a collective."""
+    lib = _lib.load()
+    n_rows, d = x_f16.shape
+    n_cols = y_f16.shape[0]
+    dev = x_f16.device
+    assert n_rows == window.rows * window.world and d == window.d
+    sc = as_scale_tensor(scale, dev)
+    ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+    nbytes = lib.vlpclip_grad_workspace_bytes(n_rows, n_cols, d)
+    ws = _ws(nbytes, dev)
+    parity = window.next_parity()
+    owners = window.owner_rows(parity)
+    rc = lib.vlpclip_grad_scatter(
+        x_f16.data_ptr(), x_f16.stride(0), y_f16.data_ptr(), y_f16.stride(0),
+        x_stats[0].data_ptr(), x_stats[1].data_ptr(), x_stats[2].data_ptr(),
+        y_stats[0].data_ptr(), y_stats[1].data_ptr(), y_stats[2].data_ptr(),
+        n_rows, n_cols, d, sc.data_ptr(), int(diag_shift), int(n_global), float(w_row), float(w_col),
+        owners, window.world, window.rows, ds.data_ptr() if want_dscale else None, ws.data_ptr(),
+        nbytes, _stream())
+    _lib.check(rc, "grad_scatter")
+    return parity, ds
+
+
+def _scatter_finish(window: PeerWindow, parity: int, out_mul, out_dtype, device):
+    lib = _lib.load()
+    out = torch.empty(window.rows, window.d, dtype=out_dtype, device=device)
+    rc = lib.vlpclip_slot_sum(window.slots(parity), window.world, window.rows * window.d,
+                              out_mul.data_ptr() if out_mul is not None else None,
+                              1 if out_dtype == torch.bfloat16 else 0, out.data_ptr(), _stream())
+    _lib.check(rc, "slot_sum")
+    return out
+
+
 class CudaOps:
     """The production ``ops`` of sharded.forward_plan / backward_plan: the sm_100a kernels."""
+
+    @staticmethod
+    def peer_window(group, world, rank, rows, d, device):
+        return peer_window(group, world, rank, rows, d, device)
+
+    @staticmethod
+    def grad_scatter(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
+                     window):
+        return _grad_scatter(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
+                             want_dscale, window)
+
+    @staticmethod
+    def scatter_finish(window, parity, out_mul, out_dtype, device):
+        return _scatter_finish(window, parity, out_mul, out_dtype, device)
 
     @staticmethod
     def lse_stats(x, y, scale, diag_shift):
@@ -427,6 +596,7 @@ def release_graphs() -> None:
         _GRAPHS.clear()
         import gc
         gc.collect()
+    release_peer_windows()
 
 
 import atexit as _atexit  # noqa: E402
@@ -520,8 +690,8 @@ def fused_clip_loss_from_embeddings(image_embeddings: torch.Tensor, text_embeddi
     if _operands is not None:
         i_bf16, t_bf16, i_f16, t_f16 = _operands
     world = sharded.group_info(group)[0]
-    if world > 1:
-        _reserve_sms_for_collectives()
+    if world > 1 and (PEER_RS_MODE == "0" or world > MAX_PEER_RANKS):
+        _reserve_sms_for_collectives()      # NCCL reduce-scatter overlaps with the dI kernel
     needs_grad = torch.is_grad_enabled() and (image_embeddings.requires_grad or
                                               text_embeddings.requires_grad or
                                               logit_scale.requires_grad)

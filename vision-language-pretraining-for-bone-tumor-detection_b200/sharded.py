@@ -9,8 +9,11 @@ CPU test-suite on a numpy restatement of the kernel contracts under the ``gloo``
 forward   all_gather(T_loc)                       -> T_all            (b*D bf16 per rank)
           all_gather([col ref | col l | own diag])  -> column statistics ((2N + b) fp32 per rank)
           all_reduce([sum row_loss, sum col_loss])                     (2 fp32)
-backward  reduce_scatter(dT_all partial)          -> dT_loc           (N*D fp32 per rank)
-          all_reduce(dscale)                                           (1 fp32)
+backward  dT rows stored into the owner's peer window from the kernel epilogue (NVLink, fused
+          reduce-scatter; ``ops.grad_scatter`` / ``ops.scatter_finish``), or, without peer
+          windows, reduce_scatter(dT_all partial) -> dT_loc          (N*D fp32 per rank)
+          all_reduce(dscale)                                           (1 fp32; doubles as the
+          barrier between the peer stores and the slot sum)
 
 ``ops`` contract (shapes: x [n_rows, D], y [n_cols, D]):
     lse_stats_fused(x, y, scale, diag_shift) -> (row_max, row_l, diag, col_ref, col_l)   [optional]
@@ -106,7 +109,15 @@ def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc
     lo = rank * n_loc
     d_i = d_t = ds = None
     pending = None
-    if need_t and world > 1:
+    window = None
+    if need_t and world > 1 and hasattr(ops, "peer_window"):
+        window = ops.peer_window(group, world, rank, n_loc, t_all_op.shape[1], t_all_op.device)
+    if window is not None:
+        # fused reduce-scatter: the dT kernel stores every finished row block straight into the
+        # owning rank's window over NVLink (no [N, D] partial, no NCCL kernel competing for SMs)
+        parity, ds = ops.grad_scatter(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col,
+                                      w_row, need_scale, window)
+    elif need_t and world > 1:
         # dT_all partial over the local images first, so that its fp32 reduce-scatter (the largest
         # message of the step, N*D*4 bytes per rank) runs on a side stream under the dI kernel
         d_t_all, ds = ops.grad(t_all_op, i_loc_op, c_stats, r_stats, scale, lo, n_glob, w_col, w_row,
@@ -138,10 +149,15 @@ def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc
             ds = ds_t
     if pending is not None:
         torch.cuda.current_stream().wait_stream(pending)
-    if need_t and world > 1 and out_mul is not None:
+    if need_t and world > 1 and window is None and out_mul is not None:
         d_t = d_t * out_mul
     if need_scale and world > 1:
         _dist().all_reduce(ds, group=group)
+    if window is not None:
+        if not need_scale:      # any collective every rank passes after its dT kernel will do
+            _dist().all_reduce(torch.zeros(1, device=t_all_op.device), group=group)
+        # every peer's stores have landed: sum the slots of the local window in rank order
+        d_t = ops.scatter_finish(window, parity, out_mul, out_dtypes[1], t_all_op.device)
     return d_i, d_t, ds
 
 
