@@ -54,7 +54,17 @@ def _worker(rank, world, port, n, d, ls, out_dir):
                 assert torch.equal(cur[1], first[1]) and torch.equal(cur[2], first[2])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss.item(), image_loss=il.item(),
                  text_loss=tl.item(), dI=Il.grad.cpu().numpy(), dT=Tl.grad.cpu().numpy(),
-                 dl=lsc.grad.item())
+                 dl=lsc.grad.item(), used_peer_windows=int(any(w.ok for w in VF._PEER_WINDOWS.values())))
+        # the same step with NCCL reduce-scatter instead of the fused NVLink stores: identical up
+        # to the fp32 summation order of the partials
+        VF.PEER_RS_MODE, VF._GRAPH_MODE = "0", "0"
+        Il.grad = Tl.grad = lsc.grad = None
+        loss2, _, _ = VF.fused_clip_loss_from_embeddings(Il, Tl, lsc, group=dist.group.WORLD)
+        loss2.backward()
+        torch.cuda.synchronize()
+        assert abs(loss2.item() - first[0]) <= 1e-6 * abs(first[0])
+        assert (Tl.grad - first[2]).norm() <= 1e-5 * first[2].norm()
+        assert (Il.grad - first[1]).norm() <= 1e-5 * first[1].norm()
     finally:
         try:
             VF.release_graphs()
@@ -75,6 +85,7 @@ def test_sharded_global_batch_matches_oracle(tmp_path, world, n, d, ls):
     b = n // world
     for r in range(world):
         got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        assert int(got["used_peer_windows"]) == 1, "fused reduce-scatter fell back to NCCL"
         assert abs(float(got["loss"]) - ref["loss"]) < 1e-4 * ref["loss"]
         assert abs(float(got["image_loss"]) - ref["image_loss"]) < 1e-4 * ref["image_loss"]
         assert O.rel_err(got["dI"], ref["dI"][r * b:(r + 1) * b]) < 1e-3
