@@ -118,6 +118,13 @@ int vlpclip_grad(const void* x_f16, int ldx, const void* y_f16, int ldy, const f
                  int n_global, float w_row, float w_col, const float* out_mul, int dx_bf16, void* dx,
                  float* dscale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* s = min(exp(logit_scale), 100) and ds/dlogit_scale on the device (VisionLanguageModule.py:456-457);
+ * logit_scale is one fp32 (is_f64 = 0) or fp64 (is_f64 = 1, the reference's dtype) device value. */
+int vlpclip_scale_prep(const void* logit_scale, int is_f64, float* scale, float* dscale_dls,
+                       void* stream);
+/* out3 = {loss, image_loss, text_loss} from the two (all-reduced) loss sums (:550-552) */
+int vlpclip_loss_finish(const float* sums2, int n_global, float* out3, void* stream);
+
 /* host-only: the backward's work partition for n_clusters SM pairs (see grad_bwd.cu, "stream-K").
  * seg rows = {cluster, row block, t0, t1, slot} (slot -1: whole row block, final rows written by the
  * kernel; 0 / 1: partial block of that cluster), red rows = {row block, cluster, slot} in the

@@ -30,6 +30,8 @@ _SIGNATURES = {
     "vlpclip_lse_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlpclip_loss_reduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "vlpclip_scale_prep": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "vlpclip_loss_finish": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "vlpclip_grad_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlpclip_grad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,

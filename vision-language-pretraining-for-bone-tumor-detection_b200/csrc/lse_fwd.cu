@@ -449,6 +449,27 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss,
   }
 }
 
+// s = min(exp(l), 100) and ds/dl (= exp(l) while unclamped, else 0), evaluated in double like the
+// reference's float64 logit_scale parameter (VisionLanguageModule.py:111, :456-457)
+__global__ void scale_prep_kernel(const void* __restrict__ logit_scale, int is_f64,
+                                  float* __restrict__ scale, float* __restrict__ dscale_dls) {
+  const double l = is_f64 ? *reinterpret_cast<const double*>(logit_scale)
+                          : (double)*reinterpret_cast<const float*>(logit_scale);
+  const double e = exp(l);
+  scale[0] = (float)(e > 100.0 ? 100.0 : e);
+  dscale_dls[0] = e <= 100.0 ? (float)e : 0.f;   // NaN propagates through both
+  if (e != e) scale[0] = (float)e;
+}
+
+// (image_loss, text_loss) = sums / N, loss = (image_loss + text_loss) / 2   (reference :550-552)
+__global__ void loss_finish_kernel(const float* __restrict__ sums2, float inv_n,
+                                   float* __restrict__ out3) {
+  const float il = sums2[0] * inv_n, tl = sums2[1] * inv_n;
+  out3[0] = (il + tl) * 0.5f;
+  out3[1] = il;
+  out3[2] = tl;
+}
+
 __global__ void cast_bf16_to_f16_kernel(const __nv_bfloat16* __restrict__ src,
                                         __half* __restrict__ dst, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,6 +668,23 @@ int vlpclip_loss_reduce(const float* row_loss, const float* col_loss, int n, flo
   if (n <= 0) return fail(-1, "loss_reduce: empty input");
   if (!out2) return fail(-1, "loss_reduce: null pointer");
   loss_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, col_loss, n, out2);
+  VLP_COUNT_LAUNCH(1);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int vlpclip_scale_prep(const void* logit_scale, int is_f64, float* scale, float* dscale_dls,
+                       void* stream) {
+  if (!logit_scale || !scale || !dscale_dls) return fail(-1, "scale_prep: null pointer");
+  scale_prep_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(logit_scale, is_f64, scale, dscale_dls);
+  VLP_COUNT_LAUNCH(1);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int vlpclip_loss_finish(const float* sums2, int n_global, float* out3, void* stream) {
+  if (!sums2 || !out3 || n_global <= 0) return fail(-1, "loss_finish: bad arguments");
+  loss_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums2, 1.0f / (float)n_global, out3);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;

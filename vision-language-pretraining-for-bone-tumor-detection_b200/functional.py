@@ -72,6 +72,21 @@ def as_scale_tensor(scale, device) -> torch.Tensor:
     return torch.full((1,), float(scale), dtype=torch.float32, device=device)
 
 
+def scale_from_logit_scale(logit_scale: torch.Tensor):
+    """(s, ds/dl) = (min(e^l, 100), e^l or 0) as fp32 device scalars, one launch, no host sync
+    (reference :456-457; evaluated in double like the reference's float64 parameter)."""
+    lib = _lib.load()
+    ls = logit_scale.detach().reshape(1)
+    if ls.dtype not in (torch.float32, torch.float64):
+        ls = ls.double()
+    ls = ls.contiguous()
+    out = torch.empty(2, dtype=torch.float32, device=ls.device)
+    rc = lib.vlpclip_scale_prep(ls.data_ptr(), 1 if ls.dtype == torch.float64 else 0,
+                                out.data_ptr(), out.data_ptr() + 4, _stream())
+    _lib.check(rc, "scale_prep")
+    return out[0:1], out[1:2]
+
+
 def cast_bf16_to_f16(src: torch.Tensor) -> torch.Tensor:
     """fp16 copy of bf16 embeddings (operands of the backward GEMMs)."""
     _require_cuda(src, "src")
@@ -180,6 +195,14 @@ def _loss_sums(row_loss: torch.Tensor, col_loss: torch.Tensor) -> torch.Tensor:
                                  out2.data_ptr(), _stream())
     _lib.check(rc, "loss_reduce")
     return out2
+
+
+def _loss_finish(sums: torch.Tensor, n_global: int) -> torch.Tensor:
+    lib = _lib.load()
+    out3 = torch.empty(3, dtype=torch.float32, device=sums.device)
+    rc = lib.vlpclip_loss_finish(sums.data_ptr(), int(n_global), out3.data_ptr(), _stream())
+    _lib.check(rc, "loss_finish")
+    return out3
 
 
 def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_global: int,
@@ -400,6 +423,10 @@ class CudaOps:
         return _loss_sums(row_loss, col_loss)
 
     @staticmethod
+    def loss_finish(sums, n_global):
+        return _loss_finish(sums, n_global)
+
+    @staticmethod
     def grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
              out_mul=None, out_dtype=torch.float32):
         return _grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
@@ -438,10 +465,8 @@ class _FusedClipLoss(torch.autograd.Function):
 
         # reference :456-457 -- exp + clamp(max=100), evaluated ON THE DEVICE (no host sync): the
         # kernels read s through a pointer
-        exp_ls = logit_scale.detach().double().exp().reshape(1)
-        scale = torch.clamp(exp_ls, max=LOGIT_SCALE_MAX).float()
-        # d/dl clamp(e^l, max=100) = e^l if e^l <= 100 else 0
-        dscale_dls = torch.where(exp_ls <= LOGIT_SCALE_MAX, exp_ls, torch.zeros_like(exp_ls)).float()
+        # (d/dl clamp(e^l, max=100) = e^l if e^l <= 100 else 0)
+        scale, dscale_dls = scale_from_logit_scale(logit_scale)
 
         if i_bf16 is None:
             i_bf16 = image_embeddings.detach().to(torch.bfloat16).contiguous()
@@ -544,44 +569,97 @@ _GRAPHS = {}
 GRAPH_REPLAYED_LAUNCHES = 0    # kernels of this library launched through graph replays
 
 
-def _fwd_bwd_eager(i_bf16, t_bf16, logit_scale, group, need_i, need_t, need_ls):
-    """losses [3] = (loss, image_loss, text_loss) and fp32 gradients of the loss (upstream = 1)."""
-    exp_ls = logit_scale.detach().double().exp().reshape(1)
-    scale = torch.clamp(exp_ls, max=LOGIT_SCALE_MAX).float()
-    dscale_dls = torch.where(exp_ls <= LOGIT_SCALE_MAX, exp_ls, torch.zeros_like(exp_ls)).float()
+def _kernel_dtype(dt):
+    return dt if dt in (torch.float32, torch.bfloat16) else torch.float32
+
+
+def _graph_forward(i_bf16, t_bf16, logit_scale, group, needs):
+    """Forward half of a graphed step: the three losses plus everything the backward half reads."""
+    scale, dscale_dls = scale_from_logit_scale(logit_scale)
     plan = sharded.forward_plan(CudaOps, i_bf16, t_bf16, scale, group, exact_columns=EXACT_COLUMNS)
-    losses = torch.stack([plan["loss"], plan["image_loss"], plan["text_loss"]])
-    d_i = d_t = d_ls = None
-    if need_i or need_t or need_ls:
-        i_f16 = CudaOps.to_backward_operand(i_bf16)
-        t_all_f16 = CudaOps.to_backward_operand(plan["t_all"])
-        d_i, d_t, ds = sharded.backward_plan(
-            CudaOps, i_f16, t_all_f16, plan["r_stats"], plan["c_stats"], scale, plan["n_loc"],
-            plan["n_glob"], plan["rank"], plan["world"], group, 1.0, 1.0, need_i, need_t, need_ls)
-        if need_ls:
-            d_ls = ds * dscale_dls
-    return losses, d_i, d_t, d_ls
+    out = {"losses": plan["losses"], "plan": plan, "scale": scale, "dscale_dls": dscale_dls}
+    if any(needs):
+        out["i_f16"] = CudaOps.to_backward_operand(i_bf16)
+        out["t_all_f16"] = CudaOps.to_backward_operand(plan["t_all"])
+    return out
+
+
+def _graph_backward(fo, g, group, needs, in_dtypes, ls_shape):
+    """Backward half: final gradients (upstream gradient ``g`` folded into the kernel epilogues)."""
+    plan = fo["plan"]
+    need_i, need_t, need_ls = needs
+    d_i, d_t, ds = sharded.backward_plan(
+        CudaOps, fo["i_f16"], fo["t_all_f16"], plan["r_stats"], plan["c_stats"], fo["scale"],
+        plan["n_loc"], plan["n_glob"], plan["rank"], plan["world"], group, 1.0, 1.0, need_i, need_t,
+        need_ls, out_mul=g, out_dtypes=(_kernel_dtype(in_dtypes[0]), _kernel_dtype(in_dtypes[1])))
+    d_ls = None
+    if need_ls:
+        d_ls = (ds * fo["dscale_dls"] * g).to(in_dtypes[2]).reshape(ls_shape)
+    if d_i is not None and d_i.dtype != in_dtypes[0]:
+        d_i = d_i.to(in_dtypes[0])
+    if d_t is not None and d_t.dtype != in_dtypes[1]:
+        d_t = d_t.to(in_dtypes[1])
+    return d_i, d_t, d_ls
 
 
 class _GraphEntry:
-    def __init__(self, n_loc, d, device, ls_dtype, group, needs):
+    """Static buffers + the two captured graphs (forward half / backward half) of one step shape.
+
+    Call 1 runs both halves eagerly (warm-up: workspaces, peer windows, NCCL channels); call 2
+    captures each half the first time it runs; later calls replay."""
+
+    def __init__(self, n_loc, d, device, in_dtypes, ls_shape, group, needs):
         self.i = torch.zeros(n_loc, d, dtype=torch.bfloat16, device=device)
         self.t = torch.zeros(n_loc, d, dtype=torch.bfloat16, device=device)
-        self.ls = torch.zeros(1, dtype=ls_dtype, device=device)
+        self.ls = torch.zeros(1, dtype=in_dtypes[2] if in_dtypes[2] == torch.float64
+                              else torch.float32, device=device)
+        self.g = torch.ones(1, dtype=torch.float32, device=device)   # upstream gradient * grad_scale
         self.group, self.needs = group, needs
-        self.graph = None
-        self.out = None
+        self.in_dtypes, self.ls_shape = in_dtypes, ls_shape
+        self.fwd_graph = self.bwd_graph = None
+        self.fwd_out = self.bwd_out = None
+        self.launches = [0, 0]   # kernels of this library per replay (forward, backward)
         self.calls = 0
-        self.generation = 0      # bumped by every forward: guards the shared gradient buffers
+        self.generation = 0      # bumped by every forward: guards the shared static buffers
 
-    def capture(self):
+    def _capture(self, fn, pool=None):
         lib = _lib.load()
         before = lib.vlpclip_launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.out = _fwd_bwd_eager(self.i, self.t, self.ls, self.group, *self.needs)
-        self.graph = g
-        self.kernel_launches = int(lib.vlpclip_launch_count() - before)   # replayed every step
+        with torch.cuda.graph(g, pool=pool):
+            out = fn()
+        return g, out, int(lib.vlpclip_launch_count() - before)
+
+    def forward(self):
+        global GRAPH_REPLAYED_LAUNCHES
+        self.calls += 1
+        run = lambda: _graph_forward(self.i, self.t, self.ls, self.group, self.needs)  # noqa: E731
+        if self.fwd_graph is None and self.calls >= 2:
+            self.fwd_graph, self.fwd_out, self.launches[0] = self._capture(run)
+        if self.fwd_graph is not None:
+            self.fwd_graph.replay()
+            GRAPH_REPLAYED_LAUNCHES += self.launches[0]
+        else:
+            self.fwd_out = run()
+        return self.fwd_out["losses"]
+
+    def backward(self):
+        global GRAPH_REPLAYED_LAUNCHES
+        run = lambda: _graph_backward(self.fwd_out, self.g, self.group, self.needs,  # noqa: E731
+                                      self.in_dtypes, self.ls_shape)
+        if self.bwd_graph is None and self.fwd_graph is not None:
+            # (its inputs are the static outputs of the captured forward half)
+            self.bwd_graph, self.bwd_out, self.launches[1] = self._capture(run, self.fwd_graph.pool())
+        if self.bwd_graph is not None:
+            self.bwd_graph.replay()
+            GRAPH_REPLAYED_LAUNCHES += self.launches[1]
+        else:
+            self.bwd_out = run()
+        return self.bwd_out
+
+    def drop(self):
+        self.fwd_graph = self.bwd_graph = None
+        self.fwd_out = self.bwd_out = None
 
 
 def release_graphs() -> None:
@@ -591,8 +669,7 @@ def release_graphs() -> None:
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         for entry in _GRAPHS.values():      # autograd contexts may still reference the entry
-            entry.graph = None
-            entry.out = None
+            entry.drop()
         _GRAPHS.clear()
         import gc
         gc.collect()
@@ -620,32 +697,20 @@ class _FusedClipLossGraphed(torch.autograd.Function):
         dev = image_embeddings.device
         needs = (image_embeddings.requires_grad, text_embeddings.requires_grad,
                  logit_scale.requires_grad)
-        key = (n_loc, d, dev.index, logit_scale.dtype, id(group), needs)
+        in_dtypes = (image_embeddings.dtype, text_embeddings.dtype, logit_scale.dtype)
+        key = (n_loc, d, dev.index, in_dtypes, tuple(logit_scale.shape), id(group), needs)
         entry = _GRAPHS.get(key)
         if entry is None:
-            entry = _GRAPHS[key] = _GraphEntry(n_loc, d, dev, logit_scale.dtype, group, needs)
+            entry = _GRAPHS[key] = _GraphEntry(n_loc, d, dev, in_dtypes, logit_scale.shape, group,
+                                               needs)
         entry.i.copy_(image_embeddings.detach())
         entry.t.copy_(text_embeddings.detach())
         entry.ls.copy_(logit_scale.detach().reshape(1))
-        entry.calls += 1
-        if entry.graph is None and entry.calls >= 2:
-            entry.capture()                      # (the first call ran eagerly = warm-up)
-        if entry.graph is not None:
-            global GRAPH_REPLAYED_LAUNCHES
-            entry.graph.replay()
-            GRAPH_REPLAYED_LAUNCHES += entry.kernel_launches
-            losses, d_i, d_t, d_ls = entry.out
-        else:
-            losses, d_i, d_t, d_ls = _fwd_bwd_eager(entry.i, entry.t, entry.ls, group, *needs)
-        # the graph's outputs are overwritten by the next replay: the three losses are copied out
-        # here; the gradients stay in place and backward checks that no other forward ran in between
-        losses = losses.clone()
+        # the static loss buffer is overwritten by the next replay: hand out a copy
+        losses = entry.forward().clone()
         entry.generation += 1
         ctx.entry, ctx.generation = entry, entry.generation
-        ctx.grads = (d_i, d_t, d_ls)
         ctx.grad_scale = float(grad_scale)
-        ctx.in_dtypes = (image_embeddings.dtype, text_embeddings.dtype, logit_scale.dtype)
-        ctx.ls_shape = logit_scale.shape
         return losses[0], losses[1], losses[2]
 
     @staticmethod
@@ -656,21 +721,17 @@ class _FusedClipLossGraphed(torch.autograd.Function):
                 "(VLP_B200_CUDA_GRAPH=0): the graph computes the gradients of `loss`")
         if g_loss is None:
             return (None,) * 5
-        if ctx.entry.generation != ctx.generation:
+        entry = ctx.entry
+        if entry.generation != ctx.generation or entry.fwd_out is None:
             raise RuntimeError(
                 "fused CLIP loss (CUDA-graph mode): another forward of the same shape ran before this "
-                "backward and overwrote the gradient buffers; set VLP_B200_CUDA_GRAPH=0 for such "
+                "backward and overwrote the saved statistics; set VLP_B200_CUDA_GRAPH=0 for such "
                 "schedules")
-        g = g_loss.detach().float() * ctx.grad_scale
-        d_i, d_t, d_ls = ctx.grads
-        out = [None, None, None, None, None]
-        if d_i is not None and ctx.needs_input_grad[0]:
-            out[0] = (d_i * g).to(ctx.in_dtypes[0])
-        if d_t is not None and ctx.needs_input_grad[1]:
-            out[1] = (d_t * g).to(ctx.in_dtypes[1])
-        if d_ls is not None and ctx.needs_input_grad[2]:
-            out[2] = (d_ls * g).to(ctx.in_dtypes[2]).reshape(ctx.ls_shape)
-        return tuple(out)
+        torch.mul(g_loss.detach().reshape(1).to(torch.float32), ctx.grad_scale, out=entry.g)
+        # gradients live in static buffers that the next backward of this shape overwrites
+        d_i, d_t, d_ls = entry.backward()
+        return (d_i if ctx.needs_input_grad[0] else None, d_t if ctx.needs_input_grad[1] else None,
+                d_ls if ctx.needs_input_grad[2] else None, None, None)
 
 
 def fused_clip_loss_from_embeddings(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor,

@@ -26,6 +26,7 @@ backward  dT rows stored into the owner's peer window from the kernel epilogue (
         diag[i] = <x_i, y_{i-diag_shift}> or 0 when that column does not exist.
     merge_stats(part_max [P,n], part_l [P,n], diag [n], scale) -> (max, lg2l, q, row_loss)
     loss_sums(row_loss, col_loss) -> 2-vector
+    loss_finish(sums, n_global) -> (loss, image_loss, text_loss) 3-vector                  [optional]
     grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale) -> (dx, ds)
     to_backward_operand(x) -> operand copy used by grad (fp16 on the GPU)
 """
@@ -91,9 +92,12 @@ def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: boo
     sums = ops.loss_sums(r_loss, c_loss[lo:lo + n_loc])
     if world > 1:
         _dist().all_reduce(sums, group=group)
-    losses = sums / float(n_glob)
-    return {"image_loss": losses[0], "text_loss": losses[1],
-            "loss": (losses[0] + losses[1]) * 0.5,            # reference :552
+    if hasattr(ops, "loss_finish"):
+        l3 = ops.loss_finish(sums, n_glob)                     # (loss, image_loss, text_loss)
+    else:
+        losses = sums / float(n_glob)
+        l3 = torch.stack([(losses[0] + losses[1]) * 0.5, losses[0], losses[1]])   # reference :552
+    return {"loss": l3[0], "image_loss": l3[1], "text_loss": l3[2], "losses": l3,
             "t_all": t_all, "r_stats": (r_max, r_lg, r_q), "c_stats": (c_max, c_lg, c_q),
             "world": world, "rank": rank, "n_loc": n_loc, "n_glob": n_glob}
 
