@@ -35,6 +35,8 @@ constexpr int C_STAGE_BYTES = 32768;
 constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
 constexpr int G_SLOT_BYTES = 32768;         // [128 rows x 128 q] fp16
 constexpr int G_SLOTS = 2;
+constexpr int BAR_BYTES = 1024;               // barrier block
+constexpr int EPI_STAGE_BYTES = 4 * 4096;    // consumer epilogue: one 32 x 32 fp32 tile per warp
 constexpr uint32_t BWD_TMEM_X = 0;          // producer: X block (fp16 packed), d/2 columns
 // producer S buffers (128 columns each) at the top of TMEM: two while d <= 512, one for d <= 768
 constexpr float G_SCALE = 8192.f;           // 2^13: keeps softmax tails out of fp16 subnormals
@@ -243,6 +245,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
       reinterpret_cast<BwdBarriers*>(smem + RING_BYTES + G_SLOTS * G_SLOT_BYTES);
   const uint32_t ring = smem_u32(smem);
   const uint32_t gslots = ring + RING_BYTES;
+  const uint32_t stage = gslots + G_SLOTS * G_SLOT_BYTES + BAR_BYTES;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -553,65 +556,77 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     } else if (warp < 6) {
       // ---- epilogue: TMEM accumulator -> global ----
       const uint32_t quarter = warp & 3;
-      const uint32_t row_in_blk = quarter * 32 + lane;
       const uint32_t lane_addr = (quarter * 32u) << 16;
       uint32_t item_ctr = 0;
       WorkRange work(cluster_id, n_clusters, p.n_row_blocks, p.total_tiles);
       Segment sg;
       for (; work.next(sg); ++item_ctr) {
-        const int row = sg.rb * 128 + row_in_blk;
         mbar_wait(smem_u32(&bars->acc_full), item_ctr & 1);
         tc_fence_after();
         const bool final_out = sg.slot < 0;
         const float mulv =
             scale_dev * ((final_out && p.out_mul) ? p.out_scale * __ldg(p.out_mul) : p.out_scale);
-        float* orow;
-        __nv_bfloat16* orow_b;
-        if (final_out) {
-          uint8_t* base;
-          const size_t r = scatter_row(p.scatter, row < p.n_rows ? row : 0, base, p.dx);
-          orow = reinterpret_cast<float*>(base) + r * p.d;
-          orow_b = reinterpret_cast<__nv_bfloat16*>(base) + r * p.d;
-        } else {
-          orow = p.part + ((size_t)(cluster_id * 2 + sg.slot) * 128 + row_in_blk) * p.d;
-          orow_b = nullptr;
+        // Each lane owns one accumulator row (TMEM lane), but rows are 2 KB apart in memory: the
+        // 32 x 32 fp32 chunk goes through a swizzled smem tile so that every store instruction
+        // writes four full 128-byte lines (matters most for the NVLink peer stores).
+        const int sub = lane >> 3, ch = lane & 7;
+        uint8_t* orow8[8];   // destination row of (i * 4 + sub), i = 0..7
+        bool ok8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + sub;
+          const int grow = sg.rb * 128 + (int)quarter * 32 + r;
+          ok8[i] = grow < p.n_rows;
+          if (final_out) {
+            uint8_t* base;
+            const size_t rr = scatter_row(p.scatter, ok8[i] ? grow : 0, base, p.dx);
+            orow8[i] = base + rr * p.d * (p.dx_bf16 ? 2 : 4);
+          } else {
+            orow8[i] = reinterpret_cast<uint8_t*>(
+                p.part + ((size_t)(cluster_id * 2 + sg.slot) * 128 + quarter * 32 + r) * p.d);
+          }
         }
+        const bool as_bf16 = final_out && p.dx_bf16;
+        const uint32_t stg = stage + (warp - 2) * 4096;
         const int cbase = p.db0 * 64;   // first dX column of this pass
         for (int cc = 0; cc < p.ndb * 64; cc += 32) {
           uint32_t v[32];
           tmem_ld_x32(tmem + lane_addr + cc, v);
           tmem_ld_wait();
-          const int c = cbase + cc;
-          if (row < p.n_rows) {
-            if (final_out && p.dx_bf16) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                if (c + j < p.d) {
-                  uint4 o;
-                  __nv_bfloat162 b;
-                  b = __floats2bfloat162_rn(__uint_as_float(v[j + 0]) * mulv, __uint_as_float(v[j + 1]) * mulv);
-                  o.x = *reinterpret_cast<uint32_t*>(&b);
-                  b = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) * mulv, __uint_as_float(v[j + 3]) * mulv);
-                  o.y = *reinterpret_cast<uint32_t*>(&b);
-                  b = __floats2bfloat162_rn(__uint_as_float(v[j + 4]) * mulv, __uint_as_float(v[j + 5]) * mulv);
-                  o.z = *reinterpret_cast<uint32_t*>(&b);
-                  b = __floats2bfloat162_rn(__uint_as_float(v[j + 6]) * mulv, __uint_as_float(v[j + 7]) * mulv);
-                  o.w = *reinterpret_cast<uint32_t*>(&b);
-                  *reinterpret_cast<uint4*>(orow_b + c + j) = o;
-                }
-            } else {
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t a = stg + lane * 128 + ((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a),
+                         "f"(__uint_as_float(v[c * 4 + 0]) * mulv),
+                         "f"(__uint_as_float(v[c * 4 + 1]) * mulv),
+                         "f"(__uint_as_float(v[c * 4 + 2]) * mulv),
+                         "f"(__uint_as_float(v[c * 4 + 3]) * mulv)
+                         : "memory");
+          }
+          __syncwarp();
+          const int col = cbase + cc + ch * 4;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (c + j < p.d) {
-                  float4 o;
-                  o.x = __uint_as_float(v[j + 0]) * mulv;
-                  o.y = __uint_as_float(v[j + 1]) * mulv;
-                  o.z = __uint_as_float(v[j + 2]) * mulv;
-                  o.w = __uint_as_float(v[j + 3]) * mulv;
-                  *reinterpret_cast<float4*>(orow + c + j) = o;
-                }
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + sub;
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                         : "r"(stg + r * 128 + ((ch ^ (r & 7)) << 4))
+                         : "memory");
+            if (ok8[i] && col < p.d) {
+              if (as_bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
+                uint2 w;
+                w.x = *reinterpret_cast<uint32_t*>(&lo);
+                w.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(orow8[i] + (size_t)col * 2) = w;
+              } else {
+                *reinterpret_cast<float4*>(orow8[i] + (size_t)col * 4) = o;
+              }
             }
           }
+          __syncwarp();
         }
         tc_fence_before();
         __syncwarp();
@@ -892,7 +907,8 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   rc = make_tmap_sw128(&map_mn, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 64);
   if (rc) return rc;
 
-  const size_t smem = RING_BYTES + G_SLOTS * G_SLOT_BYTES + sizeof(BwdBarriers) + 1024;
+  static_assert(sizeof(BwdBarriers) <= BAR_BYTES, "barrier block");
+  const size_t smem = RING_BYTES + G_SLOTS * G_SLOT_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     VLP_CUDA_OK(cudaFuncSetAttribute(grad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
