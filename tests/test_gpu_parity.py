@@ -308,3 +308,81 @@ def test_largest_sweep_size_properties(VF):
     # the sampled per-pair losses bracket the global mean
     est = 0.5 * (img_rows.mean().item() + txt_rows.mean().item())
     assert abs(est - a["loss"]) < 0.25 * a["loss"]
+
+
+# ---- small entry points added for the sharded / graphed step -----------------------------------
+DEV = torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("ls", [math.log(1 / 0.07), math.log(50.0), math.log(100.0) - 1e-3, 5.0, -3.0])
+def test_scale_prep_matches_reference_exp_clamp(VF, dtype, ls):
+    """reference :456-457: s = clamp(exp(l), max=100); ds/dl = exp(l) below the clamp, else 0."""
+    l = torch.tensor([ls], dtype=dtype, device=DEV, requires_grad=True)
+    s_ref = torch.clamp(l.exp(), max=100)
+    s_ref.backward()
+    s, ds = VF.scale_from_logit_scale(l)
+    assert s.dtype == torch.float32 and ds.dtype == torch.float32
+    assert abs(s.item() - s_ref.item()) <= 1e-6 * abs(s_ref.item())
+    assert abs(ds.item() - l.grad.item()) <= 1e-6 * max(abs(l.grad.item()), 1e-30)
+
+
+def test_slot_sum_is_an_ordered_sum(VF):
+    from vlp_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    slots = torch.randn(5, 300, 72, generator=g).to(DEV)
+    mul = torch.tensor([0.37], device=DEV)
+    want = slots[0].clone()
+    for s in range(1, 5):
+        want += slots[s]
+    want = want * mul
+    for out_dtype in (torch.float32, torch.bfloat16):
+        out = torch.empty(300, 72, dtype=out_dtype, device=DEV)
+        rc = lib.vlpclip_slot_sum(slots.data_ptr(), 5, 300 * 72, mul.data_ptr(),
+                                  1 if out_dtype == torch.bfloat16 else 0, out.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.vlpclip_last_error()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want.to(out_dtype))
+
+
+@pytest.mark.parametrize("n,d,owners", [(1000, 72, 4), (4096, 512, 8), (384, 128, 3)])
+def test_grad_scatter_routes_rows_to_their_owner(VF, n, d, owners):
+    """The fused reduce-scatter's store side on ONE device: owner buffers are slices of a local
+    tensor, so the scattered result must equal vlpclip_grad's rows, bit for bit."""
+    import ctypes
+
+    from vlp_b200 import _lib
+    lib = _lib.load()
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=11)
+    s = math.exp(2.6593)
+    i16 = VF.cast_bf16_to_f16(I.to(DEV).to(torch.bfloat16))
+    t16 = VF.cast_bf16_to_f16(T.to(DEV).to(torch.bfloat16))
+    rm, rl, rdiag = VF.lse_stats(I.to(DEV).to(torch.bfloat16), T.to(DEV).to(torch.bfloat16), s, 0)
+    cm, cl, cdiag = VF.lse_stats(T.to(DEV).to(torch.bfloat16), I.to(DEV).to(torch.bfloat16), s, 0)
+    r_stats = VF.merge_stats(rm, rl, rdiag, s)[:3]
+    c_stats = VF.merge_stats(cm, cl, cdiag, s)[:3]
+    want, ds_want = VF._grad(i16, t16, r_stats, c_stats, s, 0, n, 1.0, 1.0, True)
+    rows_per_owner = -(-n // owners)
+    # every owner gets its own (deliberately shuffled) region of one big buffer
+    pool = torch.full((owners, rows_per_owner, d), float("nan"), device=DEV)
+    order = list(reversed(range(owners)))
+    ptrs = (ctypes.c_void_p * owners)(*[pool[order[o]].data_ptr() for o in range(owners)])
+    sc = VF.as_scale_tensor(s, i16.device)
+    ds = torch.zeros(1, device=DEV)
+    nbytes = lib.vlpclip_grad_workspace_bytes(n, n, d)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    rc = lib.vlpclip_grad_scatter(
+        i16.data_ptr(), i16.stride(0), t16.data_ptr(), t16.stride(0), r_stats[0].data_ptr(),
+        r_stats[1].data_ptr(), r_stats[2].data_ptr(), c_stats[0].data_ptr(), c_stats[1].data_ptr(),
+        c_stats[2].data_ptr(), n, n, d, sc.data_ptr(), 0, n, 1.0, 1.0, ptrs, owners, rows_per_owner,
+        ds.data_ptr(), ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.vlpclip_last_error()
+    torch.cuda.synchronize()
+    for o in range(owners):
+        lo, hi = o * rows_per_owner, min(n, (o + 1) * rows_per_owner)
+        got = pool[order[o]][:hi - lo]
+        assert torch.equal(got, want[lo:hi]), f"owner {o}"
+        assert torch.isnan(pool[order[o]][hi - lo:]).all()        # rows past n are never written
+    assert ds.item() == ds_want.item()

@@ -722,7 +722,7 @@ __global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __re
 
 // Row blocks whose column sweep was split between clusters: dx rows = mul * (sum of the partial
 // blocks in cluster order).  One block row of the grid per row block; unsplit ones return at once.
-constexpr int RED_SPLIT = 8;
+constexpr int RED_SPLIT = 32;
 __global__ void dx_reduce_kernel(const float* __restrict__ part, int n_clusters, int n_row_blocks,
                                  int tiles, int n_rows, int d, const float* __restrict__ out_mul,
                                  int out_bf16, void* __restrict__ dx, const RowScatter scatter) {

@@ -383,39 +383,53 @@ __global__ void lse_merge_kernel(const float* __restrict__ part_m, const float* 
 
 // Fused forward: merge the per-row-block column partials (log2-domain reference, l) of one column
 // in fixed order and convert to the (raw max, l) convention of lse_merge_kernel.
-__global__ void col_merge_kernel(const float* __restrict__ col_ref, const float* __restrict__ col_l,
-                                 int n_row_blocks, size_t stride, int n_cols,
-                                 const float* __restrict__ scale_ptr,
-                                 float* __restrict__ out_max, float* __restrict__ out_l) {
-  // block = 32 columns x 8 row-block slices; slices are combined through smem in fixed order
-  __shared__ float sm[8][32], sl[8][32];
-  const int j = blockIdx.x * 32 + threadIdx.x;
+constexpr int CM_SLICES = 16;   // row-block slices per block
+__device__ __forceinline__ void col_merge_step(float& M, float& L, float rr, float ll) {
+  if (rr != -INFINITY) {
+    const float Mn = fmaxf(M, rr);
+    L = L * exp2f(M - Mn) + ll * exp2f(rr - Mn);   // exp2f(-inf) = 0 on the first term
+    M = Mn;
+  }
+}
+__global__ void __launch_bounds__(32 * CM_SLICES)
+col_merge_kernel(const float* __restrict__ col_ref, const float* __restrict__ col_l,
+                 int n_row_blocks, size_t stride, int n_cols,
+                 const float* __restrict__ scale_ptr, float* __restrict__ out_max,
+                 float* __restrict__ out_l) {
+  // block = 128 columns (4 per lane, 16-byte loads) x CM_SLICES row-block slices; the slices are
+  // combined through smem in fixed order.  `stride` and the column count are multiples of 128
+  // in the workspace layout, so the vector loads never leave the partial arrays.
+  __shared__ float sm[CM_SLICES][128], sl[CM_SLICES][128];
+  const int j0 = blockIdx.x * 128 + threadIdx.x * 4;
   const int slice = threadIdx.y;
   const float scale_log2 = __ldg(scale_ptr) * kLog2e;
-  float M = -INFINITY, L = 0.f;
-  if (j < n_cols) {
-    for (int r = slice; r < n_row_blocks; r += 8) {
-      const float rr = col_ref[(size_t)r * stride + j];
-      const float ll = col_l[(size_t)r * stride + j];
-      if (rr != -INFINITY) {
-        const float Mn = fmaxf(M, rr);
-        L = L * exp2f(M - Mn) + ll * exp2f(rr - Mn);   // exp2f(-inf) = 0 on the first term
-        M = Mn;
-      }
-    }
+  float M[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, L[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int r = slice; r < n_row_blocks; r += CM_SLICES) {
+    const float4 rr = *reinterpret_cast<const float4*>(col_ref + (size_t)r * stride + j0);
+    const float4 ll = *reinterpret_cast<const float4*>(col_l + (size_t)r * stride + j0);
+    col_merge_step(M[0], L[0], rr.x, ll.x);
+    col_merge_step(M[1], L[1], rr.y, ll.y);
+    col_merge_step(M[2], L[2], rr.z, ll.z);
+    col_merge_step(M[3], L[3], rr.w, ll.w);
   }
-  sm[slice][threadIdx.x] = M;
-  sl[slice][threadIdx.x] = L;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    sm[slice][threadIdx.x * 4 + e] = M[e];
+    sl[slice][threadIdx.x * 4 + e] = L[e];
+  }
   __syncthreads();
-  if (slice == 0 && j < n_cols) {
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int j = blockIdx.x * 128 + t;
+  if (t < 128 && j < n_cols) {
     float Mt = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) Mt = fmaxf(Mt, sm[q][threadIdx.x]);
+    for (int q = 0; q < CM_SLICES; ++q) Mt = fmaxf(Mt, sm[q][t]);
     float Lt = 0.f;
     if (Mt != -INFINITY) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (sm[q][threadIdx.x] != -INFINITY) Lt += sl[q][threadIdx.x] * exp2f(sm[q][threadIdx.x] - Mt);
+      for (int q = 0; q < CM_SLICES; ++q)
+        if (sm[q][t] != -INFINITY) Lt += sl[q][t] * exp2f(sm[q][t] - Mt);
     }
     const float mx = Mt / scale_log2;                 // surrogate "max" in raw cosine units
     out_max[j] = mx;
@@ -429,7 +443,22 @@ __global__ void loss_reduce_kernel(const float* __restrict__ row_loss,
                                    float* __restrict__ out2) {
   __shared__ double sh[2][1024];
   double a = 0.0, b = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  // 8 independent loads in flight per thread; the per-thread order is still fixed
+  int i = threadIdx.x;
+  for (; i + 7 * (int)blockDim.x < n; i += 8 * blockDim.x) {
+    float ra[8], rb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      ra[u] = row_loss ? row_loss[i + u * blockDim.x] : 0.f;
+      rb[u] = col_loss ? col_loss[i + u * blockDim.x] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a += (double)ra[u];
+      b += (double)rb[u];
+    }
+  }
+  for (; i < n; i += blockDim.x) {
     if (row_loss) a += (double)row_loss[i];
     if (col_loss) b += (double)col_loss[i];
   }
@@ -618,7 +647,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   if (fused) {
-    col_merge_kernel<<<(n_cols + 31) / 32, dim3(32, 8), 0, stream>>>(
+    col_merge_kernel<<<(n_cols + 127) / 128, dim3(32, CM_SLICES), 0, stream>>>(
         p.col_ref, p.col_l, p.n_row_blocks, col_stride, n_cols, scale, col_max, col_l);
     VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
