@@ -187,7 +187,7 @@ def run_reference(args):
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -403,7 +403,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
@@ -416,7 +416,30 @@ def _all_gather_list(t, world):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON
+    line on stdout, so everything else is sent to stderr and the line goes to the saved fd."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    text = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, text)
+    else:
+        os.write(_REAL_STDOUT, text)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
