@@ -118,6 +118,21 @@ int vlpclip_grad(const void* x_f16, int ldx, const void* y_f16, int ldy, const f
                  int n_global, float w_row, float w_col, const float* out_mul, int dx_bf16, void* dx,
                  float* dscale, void* workspace, size_t workspace_bytes, void* stream);
 
+/* the same two sweeps on fp16 operands (the backward's operand copies; bf16-representable inputs
+ * convert exactly, so the statistics are identical): lets a sharded step gather ONE fp16 copy of T */
+int vlpclip_lse_fwd_f16(const void* x_f16, int ldx, const void* y_f16, int ldy, int n_rows, int n_cols,
+                        int d, const float* scale, int diag_shift, float* row_max, float* row_l,
+                        float* diag, void* workspace, size_t workspace_bytes, void* stream);
+int vlpclip_lse_fwd_fused_f16(const void* x_f16, int ldx, const void* y_f16, int ldy, int n_rows,
+                              int n_cols, int d, const float* scale, int diag_shift, float* row_max,
+                              float* row_l, float* diag, float* col_max, float* col_l,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* bf16 -> fp16 cast of n_elems (multiple of 8) values stored to n_dst (<= 8) destinations at once.
+ * dsts is a HOST array of device pointers; with dsts[r] inside rank r's peer window this is the
+ * all-gather of the local text shard, fused into the cast that the backward needs anyway. */
+int vlpclip_cast_push_f16(const void* src_bf16, size_t n_elems, void* const* dsts, int n_dst,
+                          void* stream);
+
 /* s = min(exp(logit_scale), 100) and ds/dlogit_scale on the device (VisionLanguageModule.py:456-457);
  * logit_scale is one fp32 (is_f64 = 0) or fp64 (is_f64 = 1, the reference's dtype) device value. */
 int vlpclip_scale_prep(const void* logit_scale, int is_f64, float* scale, float* dscale_dls,

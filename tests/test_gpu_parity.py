@@ -386,3 +386,39 @@ def test_grad_scatter_routes_rows_to_their_owner(VF, n, d, owners):
         assert torch.equal(got, want[lo:hi]), f"owner {o}"
         assert torch.isnan(pool[order[o]][hi - lo:]).all()        # rows past n are never written
     assert ds.item() == ds_want.item()
+
+
+def test_forward_sweep_on_fp16_operands_matches_bf16(VF):
+    """The sharded step sweeps the fp16 operand copies (one gathered copy of T serves forward and
+    backward): bf16-representable values convert exactly, so the statistics must agree."""
+    I, T = O.make_embeddings(1500, 256, rho=0.35, seed=21)
+    s = math.exp(2.6593)
+    ib, tb = I.to(DEV).to(torch.bfloat16), T.to(DEV).to(torch.bfloat16)
+    ih, th = VF.cast_bf16_to_f16(ib), VF.cast_bf16_to_f16(tb)
+    a = VF.lse_stats_fused(ib, tb, s, 0)
+    b = VF.lse_stats_fused(ih, th, s, 0)
+    for x, y in zip(a, b):
+        assert torch.allclose(x, y, rtol=1e-6, atol=1e-7)
+    a = VF.lse_stats(tb, ib, s, 0)
+    b = VF.lse_stats(th, ih, s, 0)
+    for x, y in zip(a, b):
+        assert torch.allclose(x, y, rtol=1e-6, atol=1e-7)
+
+
+def test_cast_push_writes_every_destination(VF):
+    import ctypes
+
+    from vlp_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    src = torch.randn(777, 72, generator=g).to(DEV).to(torch.bfloat16)
+    want = VF.cast_bf16_to_f16(src)
+    pool = torch.zeros(3, 1000, 72, dtype=torch.float16, device=DEV)
+    ptrs = (ctypes.c_void_p * 3)(*[pool[r, 100:].data_ptr() for r in range(3)])
+    rc = lib.vlpclip_cast_push_f16(src.data_ptr(), src.numel(), ptrs, 3,
+                                   torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.vlpclip_last_error()
+    torch.cuda.synchronize()
+    for r in range(3):
+        assert torch.equal(pool[r, 100:877], want)
+        assert (pool[r, :100] == 0).all() and (pool[r, 877:] == 0).all()

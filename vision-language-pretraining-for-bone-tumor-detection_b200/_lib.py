@@ -27,6 +27,12 @@ _SIGNATURES = {
     "vlpclip_lse_fwd_fused": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                       c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_void_p]),
+    "vlpclip_lse_fwd_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlpclip_lse_fwd_fused_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                          c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlpclip_cast_push_f16": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
     "vlpclip_lse_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vlpclip_loss_reduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -34,6 +34,7 @@ constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: d/2 columns (256 at d =
 // one for 512 < d <= 768 (MMA and softmax of consecutive tiles then serialise)
 
 struct LseParams {
+  int operand_f16;   // 0: X, Y are bf16; 1: fp16 (the backward's operand copies)
   const __nv_bfloat16* x;
   int ldx;
   int n_rows, n_cols, d;
@@ -130,7 +131,8 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp converged, one elected lane issues) ===========
-    const uint32_t idesc = make_idesc(UMMA_BF16, UMMA_BF16, MAJOR_K, MAJOR_K, 128, 128);
+    const uint32_t fmt = p.operand_f16 ? UMMA_F16 : UMMA_BF16;
+    const uint32_t idesc = make_idesc(fmt, fmt, MAJOR_K, MAJOR_K, 128, 128);
     uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
       const int chunk = item / p.n_row_blocks;
@@ -578,7 +580,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
                         int d, const float* scale, int diag_shift, float* row_max, float* row_l,
                         float* diag,
                         float* col_max, float* col_l, void* workspace, size_t workspace_bytes,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, bool operand_f16 = false) {
   const bool fused = col_max != nullptr;
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "lse_fwd: empty problem (%d x %d)", n_rows, n_cols);
   if (!x || !y || !scale || !row_max || !row_l || !diag || !workspace || (fused && !col_l))
@@ -596,6 +598,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
     return fail(-1, "lse_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
 
   LseParams p = {};
+  p.operand_f16 = operand_f16 ? 1 : 0;
   p.x = (const __nv_bfloat16*)x;
   p.ldx = ldx;
   p.n_rows = n_rows;
@@ -675,6 +678,68 @@ int vlpclip_lse_fwd_fused(const void* x, int ldx, const void* y, int ldy, int n_
   if (!col_max || !col_l) return fail(-1, "lse_fwd_fused: null column outputs");
   return lse_fwd_impl(x, ldx, y, ldy, n_rows, n_cols, d, scale, diag_shift, row_max, row_l, diag,
                       col_max, col_l, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+int vlpclip_lse_fwd_f16(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,
+                        int d, const float* scale, int diag_shift, float* row_max, float* row_l,
+                        float* diag, void* workspace, size_t workspace_bytes, void* stream_) {
+  return lse_fwd_impl(x, ldx, y, ldy, n_rows, n_cols, d, scale, diag_shift, row_max, row_l, diag,
+                      nullptr, nullptr, workspace, workspace_bytes, (cudaStream_t)stream_, true);
+}
+
+int vlpclip_lse_fwd_fused_f16(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,
+                              int d, const float* scale, int diag_shift, float* row_max,
+                              float* row_l, float* diag, float* col_max, float* col_l,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!col_max || !col_l) return fail(-1, "lse_fwd_fused: null column outputs");
+  return lse_fwd_impl(x, ldx, y, ldy, n_rows, n_cols, d, scale, diag_shift, row_max, row_l, diag,
+                      col_max, col_l, workspace, workspace_bytes, (cudaStream_t)stream_, true);
+}
+
+// bf16 -> fp16 cast of a local shard, stored into n_dst destinations at once: with dsts[r] pointing
+// into rank r's gather window (NVLink peer memory) at this rank's row offset, the cast IS the
+// all-gather -- every store instruction writes full 128-byte lines.
+constexpr int PUSH_MAX_DST = 8;
+struct PushDst {
+  void* p[PUSH_MAX_DST];
+};
+__global__ void cast_push_f16_kernel(const uint4* __restrict__ src, size_t n8, const PushDst dst,
+                                     int n_dst) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 v = src[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+      const __half2 h = __floats2half2_rn(__bfloat162float(b.x), __bfloat162float(b.y));
+      o[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const uint4 out = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int r = 0; r < n_dst; ++r) reinterpret_cast<uint4*>(dst.p[r])[i] = out;
+  }
+}
+
+int vlpclip_cast_push_f16(const void* src_bf16, size_t n_elems, void* const* dsts, int n_dst,
+                          void* stream) {
+  if (!src_bf16 || !dsts || n_dst <= 0 || n_dst > PUSH_MAX_DST || n_elems == 0 || n_elems % 8 != 0)
+    return fail(-1, "cast_push: bad arguments (n_elems %zu, n_dst %d)", n_elems, n_dst);
+  if ((reinterpret_cast<uintptr_t>(src_bf16) & 15) != 0)
+    return fail(-1, "cast_push: source must be 16-byte aligned");
+  PushDst d = {};
+  for (int r = 0; r < n_dst; ++r) {
+    if (!dsts[r] || (reinterpret_cast<uintptr_t>(dsts[r]) & 15) != 0)
+      return fail(-1, "cast_push: destination %d is null or not 16-byte aligned", r);
+    d.p[r] = dsts[r];
+  }
+  const size_t n8 = n_elems / 8;
+  int blocks = (int)((n8 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cast_push_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src_bf16, n8, d, n_dst);
+  VLP_COUNT_LAUNCH(1);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int vlpclip_lse_merge(const float* part_max, const float* part_l, const float* diag, int nparts,

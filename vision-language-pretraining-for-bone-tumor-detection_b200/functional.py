@@ -105,8 +105,8 @@ def lse_stats(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shi
     cosine (0 for rows without a partner column)."""
     _require_cuda(x_bf16, "x")
     _require_cuda(y_bf16, "y")
-    if x_bf16.dtype != torch.bfloat16 or y_bf16.dtype != torch.bfloat16:
-        raise ValueError("lse_stats expects bf16 operands")
+    if x_bf16.dtype != y_bf16.dtype or x_bf16.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("lse_stats expects two bf16 (or two fp16) operands")
     x = _as_2d_contig(x_bf16, "x")
     y = _as_2d_contig(y_bf16, "y")
     if x.shape[1] != y.shape[1]:
@@ -121,9 +121,10 @@ def lse_stats(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shi
     diag = torch.zeros(n_rows, dtype=torch.float32, device=dev)
     nbytes = lib.vlpclip_lse_workspace_bytes(n_rows, n_cols, d)
     ws = _ws(nbytes, dev)
-    rc = lib.vlpclip_lse_fwd(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows, n_cols, d,
-                             sc.data_ptr(), int(diag_shift), row_max.data_ptr(), row_l.data_ptr(),
-                             diag.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    fn = lib.vlpclip_lse_fwd_f16 if x.dtype == torch.float16 else lib.vlpclip_lse_fwd
+    rc = fn(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows, n_cols, d,
+            sc.data_ptr(), int(diag_shift), row_max.data_ptr(), row_l.data_ptr(),
+            diag.data_ptr(), ws.data_ptr(), nbytes, _stream())
     _lib.check(rc, "lse_fwd")
     return row_max, row_l, diag
 
@@ -133,8 +134,8 @@ def lse_stats_fused(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, di
     every column over the given rows: (row_max, row_l, diag, col_ref, col_l)."""
     _require_cuda(x_bf16, "x")
     _require_cuda(y_bf16, "y")
-    if x_bf16.dtype != torch.bfloat16 or y_bf16.dtype != torch.bfloat16:
-        raise ValueError("lse_stats_fused expects bf16 operands")
+    if x_bf16.dtype != y_bf16.dtype or x_bf16.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("lse_stats_fused expects two bf16 (or two fp16) operands")
     x = _as_2d_contig(x_bf16, "x")
     y = _as_2d_contig(y_bf16, "y")
     if x.shape[1] != y.shape[1]:
@@ -151,10 +152,10 @@ def lse_stats_fused(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, di
     col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
     nbytes = lib.vlpclip_lse_fused_workspace_bytes(n_rows, n_cols, d)
     ws = _ws(nbytes, dev)
-    rc = lib.vlpclip_lse_fwd_fused(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows,
-                                   n_cols, d, sc.data_ptr(), int(diag_shift), row_max.data_ptr(),
-                                   row_l.data_ptr(), diag.data_ptr(), col_max.data_ptr(),
-                                   col_l.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    fn = lib.vlpclip_lse_fwd_fused_f16 if x.dtype == torch.float16 else lib.vlpclip_lse_fwd_fused
+    rc = fn(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows, n_cols, d, sc.data_ptr(),
+            int(diag_shift), row_max.data_ptr(), row_l.data_ptr(), diag.data_ptr(),
+            col_max.data_ptr(), col_l.data_ptr(), ws.data_ptr(), nbytes, _stream())
     _lib.check(rc, "lse_fwd_fused")
     return row_max, row_l, diag, col_max, col_l
 
@@ -241,12 +242,25 @@ def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_globa
 # straight into the owning rank's window (CUDA IPC peer memory) instead of calling NCCL
 # reduce-scatter on a [N, D] fp32 partial.  auto = use it when every rank could map every window.
 PEER_RS_MODE = os.environ.get("VLP_B200_PEER_RS", "auto").lower()
+# VLP_B200_PUSH_GATHER=auto|1|0: all-gather the text shard by storing its fp16 operand copy into every
+# peer's window from the cast kernel (the forward then sweeps the fp16 copies); needs the windows.
+PUSH_GATHER_MODE = os.environ.get("VLP_B200_PUSH_GATHER", "auto").lower()
 MAX_PEER_RANKS = 8
 _PEER_WINDOWS = {}
 
 
+class _DeviceMemory:
+    """Zero-copy torch view of library-owned device memory (CUDA array interface)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
 class PeerWindow:
-    """fp32 window [2 parities][world slots][rows, d] on every rank, mapped into every peer.
+    """Exchange window on every rank, mapped into every peer:
+    fp32 [2 parities][world slots][rows, d] (reduce-scatter slots) followed by
+    fp16 [2 parities][world * rows, d] (gathered text operand).
 
     Rank s writes its partial of the rows owned by rank o into slot s of o's window; after a
     collective that all ranks pass, o sums its slots in slot order (``vlpclip_slot_sum``).  Two
@@ -260,13 +274,18 @@ class PeerWindow:
         self.group, self.world, self.rank = group, world, rank
         self.rows, self.d = rows, d
         self.slot_bytes = rows * d * 4
+        self.rs_bytes = 2 * world * self.slot_bytes
+        self.gather_bytes = world * rows * d * 2          # one parity of the gathered fp16 operand
         self.local = None
         self.peers = [None] * world
         self.parity = 0
+        self.gather_parity = 0
+        self.device = device
         ok = 1
         handle = (ctypes.c_ubyte * 64)()
         ptr = ctypes.c_void_p()
-        if lib.vlpclip_peer_alloc(2 * world * self.slot_bytes, ctypes.byref(ptr), handle) == 0:
+        if lib.vlpclip_peer_alloc(self.rs_bytes + 2 * self.gather_bytes, ctypes.byref(ptr),
+                                  handle) == 0:
             self.local = ptr.value
         else:
             ok = 0
@@ -288,6 +307,9 @@ class PeerWindow:
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also a barrier
         self.ok = bool(flag.item())
+        self._gathered = None
+        if self.ok:      # views are created here, never inside a CUDA-graph capture
+            self._gathered = [self._view(0), self._view(1)]
         if not self.ok:
             self.error = lib.vlpclip_last_error().decode(errors="replace")
             self.close(barrier=False)
@@ -304,6 +326,27 @@ class PeerWindow:
 
     def slots(self, parity: int) -> int:
         return self.local + parity * self.world * self.slot_bytes
+
+    def next_gather_parity(self) -> int:
+        self.gather_parity ^= 1
+        return self.gather_parity
+
+    def gather_dsts(self, parity: int):
+        """Host array: for every rank r, where THIS rank's rows live inside r's gathered operand."""
+        import ctypes
+        off = self.rs_bytes + parity * self.gather_bytes + self.rank * self.rows * self.d * 2
+        return (ctypes.c_void_p * self.world)(*[p + off for p in self.peers])
+
+    def _view(self, parity: int) -> torch.Tensor:
+        mem = _DeviceMemory(self.local + self.rs_bytes + parity * self.gather_bytes,
+                            (self.world * self.rows, self.d), "<f2")
+        t = torch.as_tensor(mem, device=self.device)
+        t._vlp_owner = mem
+        return t
+
+    def gathered(self, parity: int) -> torch.Tensor:
+        """[world * rows, d] fp16 view of the local gathered operand (no copy)."""
+        return self._gathered[parity]
 
     def close(self, barrier: bool = True):
         lib = _lib.load()
@@ -341,6 +384,28 @@ def peer_window(group, world: int, rank: int, rows: int, d: int, device) -> Opti
                 import warnings
                 warnings.warn(msg)
     return w if w.ok else None
+
+
+def _push_gather(i_loc, t_loc, group, world: int, rank: int):
+    """(I_loc fp16, T_all fp16) with T_all assembled by NVLink peer stores from the cast kernel, or
+    None when peer windows are off.  Ends with a collective every rank passes, so all shards have
+    landed when it returns (stream order)."""
+    if PUSH_GATHER_MODE == "0" or t_loc.dtype != torch.bfloat16 or i_loc.dtype != torch.bfloat16:
+        return None
+    window = peer_window(group, world, rank, t_loc.shape[0], t_loc.shape[1], t_loc.device)
+    if window is None:
+        if PUSH_GATHER_MODE == "1":
+            raise RuntimeError("VLP_B200_PUSH_GATHER=1 but peer windows are unavailable")
+        return None
+    lib = _lib.load()
+    t_loc = t_loc.contiguous()
+    parity = window.next_gather_parity()
+    rc = lib.vlpclip_cast_push_f16(t_loc.data_ptr(), t_loc.numel(), window.gather_dsts(parity),
+                                   world, _stream())
+    _lib.check(rc, "cast_push_f16")
+    i_f16 = cast_bf16_to_f16(i_loc)        # (runs while the peers' stores are in flight)
+    sharded._dist().all_reduce(torch.zeros(1, device=t_loc.device), group=group)
+    return i_f16, window.gathered(parity)
 
 
 def release_peer_windows() -> None:
@@ -395,6 +460,10 @@ class CudaOps:
     @staticmethod
     def peer_window(group, world, rank, rows, d, device):
         return peer_window(group, world, rank, rows, d, device)
+
+    @staticmethod
+    def push_gather(i_loc, t_loc, group, world, rank):
+        return _push_gather(i_loc, t_loc, group, world, rank)
 
     @staticmethod
     def grad_scatter(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
@@ -503,6 +572,9 @@ class _FusedClipLoss(torch.autograd.Function):
         ctx.ls_shape = logit_scale.shape
         ctx.save_for_backward(i_bf16, plan["t_all"], *plan["r_stats"], *plan["c_stats"])
         ctx.f16 = (i_f16, t_f16 if world == 1 else None)
+        ctx.tail_barrier = plan["bwd_operands"] is not None
+        if plan["bwd_operands"] is not None:      # the forward already swept the fp16 copies
+            ctx.f16 = plan["bwd_operands"]
         return plan["loss"], plan["image_loss"], plan["text_loss"]
 
     @staticmethod
@@ -543,7 +615,8 @@ class _FusedClipLoss(torch.autograd.Function):
         d_i, d_t, ds = sharded.backward_plan(
             CudaOps, i_f16, t_all_f16, r_stats, c_stats, ctx.scale, ctx.n_loc, ctx.n_glob, ctx.rank,
             world, ctx.group, w_r, w_c, need_i, need_t, need_ls, out_mul=mul,
-            out_dtypes=(kdt(ctx.in_dtypes[0]), kdt(ctx.in_dtypes[1])))
+            out_dtypes=(kdt(ctx.in_dtypes[0]), kdt(ctx.in_dtypes[1])),
+            tail_barrier=ctx.tail_barrier)
         d_ls = None
         if need_ls:
             d_ls = ds * ctx.dscale_dls                      # chain rule through exp + clamp (:456-457)
@@ -578,7 +651,9 @@ def _graph_forward(i_bf16, t_bf16, logit_scale, group, needs):
     scale, dscale_dls = scale_from_logit_scale(logit_scale)
     plan = sharded.forward_plan(CudaOps, i_bf16, t_bf16, scale, group, exact_columns=EXACT_COLUMNS)
     out = {"losses": plan["losses"], "plan": plan, "scale": scale, "dscale_dls": dscale_dls}
-    if any(needs):
+    if plan["bwd_operands"] is not None:      # the forward already swept the fp16 copies
+        out["i_f16"], out["t_all_f16"] = plan["bwd_operands"]
+    elif any(needs):
         out["i_f16"] = CudaOps.to_backward_operand(i_bf16)
         out["t_all_f16"] = CudaOps.to_backward_operand(plan["t_all"])
     return out
@@ -591,7 +666,8 @@ def _graph_backward(fo, g, group, needs, in_dtypes, ls_shape):
     d_i, d_t, ds = sharded.backward_plan(
         CudaOps, fo["i_f16"], fo["t_all_f16"], plan["r_stats"], plan["c_stats"], fo["scale"],
         plan["n_loc"], plan["n_glob"], plan["rank"], plan["world"], group, 1.0, 1.0, need_i, need_t,
-        need_ls, out_mul=g, out_dtypes=(_kernel_dtype(in_dtypes[0]), _kernel_dtype(in_dtypes[1])))
+        need_ls, out_mul=g, out_dtypes=(_kernel_dtype(in_dtypes[0]), _kernel_dtype(in_dtypes[1])),
+        tail_barrier=plan["bwd_operands"] is not None)
     d_ls = None
     if need_ls:
         d_ls = (ds * fo["dscale_dls"] * g).to(in_dtypes[2]).reshape(ls_shape)

@@ -6,7 +6,9 @@ orchestration runs (a) in production on the CUDA kernels (``functional.CudaOps``
 CPU test-suite on a numpy restatement of the kernel contracts under the ``gloo`` backend
 (``tests/test_distributed_cpu.py``).  Only the per-rank tile work differs; the exchange steps are:
 
-forward   all_gather(T_loc)                       -> T_all            (b*D bf16 per rank)
+forward   all_gather(T_loc)                       -> T_all            (b*D bf16 per rank), or
+          ``ops.push_gather``: the fp16 cast of T_loc stores its rows into every peer's window
+          (NVLink) and a 1-element all_reduce closes the exchange
           all_gather([col ref | col l | own diag])  -> column statistics ((2N + b) fp32 per rank)
           all_reduce([sum row_loss, sum col_loss])                     (2 fp32)
 backward  dT rows stored into the owner's peer window from the kernel epilogue (NVLink, fused
@@ -64,7 +66,15 @@ def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: boo
     n_loc = i_loc.shape[0]
     n_glob = n_loc * world
     lo = rank * n_loc
-    t_all = all_gather_rows(t_loc, group, world) if world > 1 else t_loc
+    pushed = None
+    if world > 1 and hasattr(ops, "push_gather"):
+        # the cast to the backward's operand format stores every row into all peers' windows: the
+        # all-gather rides on a kernel that has to run anyway, and one gathered copy serves both sweeps
+        pushed = ops.push_gather(i_loc, t_loc, group, world, rank)
+    if pushed is not None:
+        i_loc, t_all = pushed
+    else:
+        t_all = all_gather_rows(t_loc, group, world) if world > 1 else t_loc
 
     fused = (not exact_columns) and hasattr(ops, "lse_stats_fused")
     if fused:
@@ -98,14 +108,14 @@ def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: boo
         losses = sums / float(n_glob)
         l3 = torch.stack([(losses[0] + losses[1]) * 0.5, losses[0], losses[1]])   # reference :552
     return {"loss": l3[0], "image_loss": l3[1], "text_loss": l3[2], "losses": l3,
-            "t_all": t_all, "r_stats": (r_max, r_lg, r_q), "c_stats": (c_max, c_lg, c_q),
+            "t_all": t_all, "bwd_operands": pushed, "r_stats": (r_max, r_lg, r_q), "c_stats": (c_max, c_lg, c_q),
             "world": world, "rank": rank, "n_loc": n_loc, "n_glob": n_glob}
 
 
 def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc: int, n_glob: int,
                   rank: int, world: int, group=None, w_row: float = 1.0, w_col: float = 1.0,
                   need_i: bool = True, need_t: bool = True, need_scale: bool = True,
-                  out_mul=None, out_dtypes=(torch.float32, torch.float32)):
+                  out_mul=None, out_dtypes=(torch.float32, torch.float32), tail_barrier=False):
     """(dI_loc, dT_loc, dscale) of the global loss; operands are the backward copies.
 
     ``out_mul`` (device scalar) multiplies dI and dT (not dscale); where a gradient is final on this
@@ -157,9 +167,12 @@ def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc
         d_t = d_t * out_mul
     if need_scale and world > 1:
         _dist().all_reduce(ds, group=group)
-    if window is not None:
-        if not need_scale:      # any collective every rank passes after its dT kernel will do
+    if (window is not None or tail_barrier) and world > 1:
+        # ``tail_barrier``: the operands live in peer windows the next step's gather overwrites --
+        # no rank may get there before every rank has finished reading them
+        if not need_scale:      # any collective every rank passes after its kernels will do
             _dist().all_reduce(torch.zeros(1, device=t_all_op.device), group=group)
+    if window is not None:
         # every peer's stores have landed: sum the slots of the local window in rank order
         d_t = ops.scatter_finish(window, parity, out_mul, out_dtypes[1], t_all_op.device)
     return d_i, d_t, ds
