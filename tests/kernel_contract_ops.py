@@ -78,3 +78,61 @@ class ContractOps:
     @staticmethod
     def to_backward_operand(x):
         return x
+
+
+class _EmulatedWindow:
+    """What functional.PeerWindow is to the plan: per-parity reduce-scatter slots and gathered
+    operand; 'peer stores' are emulated with gloo collectives at the moment the kernel would run."""
+
+    def __init__(self, group, world, rank, rows, d):
+        self.group, self.world, self.rank, self.rows, self.d = group, world, rank, rows, d
+        self.slots = {}
+        self.parity = 0
+        self.log = []
+
+
+class WindowContractOps(ContractOps):
+    """ContractOps plus the optional peer-window ops of the sharded plan (push_gather,
+    peer_window / grad_scatter / scatter_finish), so that the fused-collective branches of
+    sharded.forward_plan / backward_plan run on CPU under gloo."""
+    windows = {}
+
+    @classmethod
+    def peer_window(cls, group, world, rank, rows, d, device):
+        key = (id(group), rows, d)
+        if key not in cls.windows:
+            cls.windows[key] = _EmulatedWindow(group, world, rank, rows, d)
+        return cls.windows[key]
+
+    @classmethod
+    def push_gather(cls, i_loc, t_loc, group, world, rank):
+        import torch.distributed as dist
+        w = cls.peer_window(group, world, rank, t_loc.shape[0], t_loc.shape[1], t_loc.device)
+        t_all = torch.empty(world * t_loc.shape[0], t_loc.shape[1], dtype=t_loc.dtype)
+        dist.all_gather_into_tensor(t_all, t_loc.contiguous(), group=group)   # = the peer stores
+        dist.all_reduce(torch.zeros(1), group=group)                          # closing collective
+        w.log.append("push_gather")
+        return i_loc, t_all
+
+    @classmethod
+    def grad_scatter(cls, x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
+                     want_dscale, window):
+        import torch.distributed as dist
+        dx, ds = ContractOps.grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
+                                  want_dscale)
+        window.parity ^= 1
+        # rank s stores rows [o*rows, (o+1)*rows) of its partial into slot s of owner o
+        parts = [torch.empty_like(dx) for _ in range(window.world)]
+        dist.all_gather(parts, dx.contiguous(), group=window.group)
+        lo = window.rank * window.rows
+        window.slots[window.parity] = [p[lo:lo + window.rows].clone() for p in parts]
+        window.log.append("grad_scatter")
+        return window.parity, ds
+
+    @classmethod
+    def scatter_finish(cls, window, parity, out_mul, out_dtype, device):
+        acc = window.slots[parity][0].clone()
+        for s in range(1, window.world):
+            acc += window.slots[parity][s]
+        window.log.append("scatter_finish")
+        return acc * out_mul if out_mul is not None else acc

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, d, ls, out_dir, exact):
+def _worker(rank, world, port, n, d, ls, out_dir, exact, windows=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -31,8 +31,10 @@ def _worker(rank, world, port, n, d, ls, out_dir, exact):
     try:
         import vlp_b200  # noqa: F401
         from vlp_b200 import sharded
-        from kernel_contract_ops import ContractOps
+        from kernel_contract_ops import ContractOps, WindowContractOps
         from oracle import clip_oracle as O
+        if windows:       # fused-collective branches of the plan (emulated peer windows)
+            ContractOps = WindowContractOps
         I, T = O.make_embeddings(n, d, rho=0.35, seed=42)      # every rank builds the global batch
         b = n // world
         i_loc = I[rank * b:(rank + 1) * b].double()
@@ -40,8 +42,15 @@ def _worker(rank, world, port, n, d, ls, out_dir, exact):
         scale = min(math.exp(ls), 100.0)
         plan = sharded.forward_plan(ContractOps, i_loc, t_loc, scale, dist.group.WORLD,
                                     exact_columns=exact)
+        mul = torch.tensor(0.5, dtype=torch.float64) if windows else None
         d_i, d_t, ds = sharded.backward_plan(ContractOps, i_loc, plan["t_all"], plan["r_stats"],
-                                             plan["c_stats"], scale, b, n, rank, world, dist.group.WORLD)
+                                             plan["c_stats"], scale, b, n, rank, world, dist.group.WORLD,
+                                             out_mul=mul, tail_barrier=plan["bwd_operands"] is not None)
+        if windows:
+            assert plan["bwd_operands"] is not None
+            log = next(iter(WindowContractOps.windows.values())).log
+            assert log == ["push_gather", "grad_scatter", "scatter_finish"], log
+            d_i, d_t = d_i / mul, d_t / mul          # out_mul scales dI and dT, never dscale
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=plan["loss"].numpy(),
                  image_loss=plan["image_loss"].numpy(), text_loss=plan["text_loss"].numpy(),
                  dI=d_i.numpy(), dT=d_t.numpy(), ds=ds.numpy())
@@ -63,6 +72,25 @@ def test_sharded_plan_matches_single_process_oracle(tmp_path, world, n, d, ls, e
         assert abs(float(got["loss"]) - ref["loss"]) < 1e-10          # same global loss on every rank
         assert abs(float(got["image_loss"]) - ref["image_loss"]) < 1e-10
         assert abs(float(got["text_loss"]) - ref["text_loss"]) < 1e-10
+        assert O.rel_err(got["dI"], ref["dI"][r * b:(r + 1) * b]) < 1e-10
+        assert O.rel_err(got["dT"], ref["dT"][r * b:(r + 1) * b]) < 1e-10
+        assert abs(float(got["ds"][0]) - ref["dscale"]) < 1e-10 * max(1.0, abs(ref["dscale"]))
+
+
+@pytest.mark.parametrize("world,n,d,ls", [(2, 96, 32, 2.6593), (4, 64, 16, 3.5)])
+def test_sharded_plan_with_peer_window_ops_matches_oracle(tmp_path, world, n, d, ls):
+    """Same check through the fused-collective branches (push-gather, row scatter into owner slots,
+    slot sum in rank order, upstream gradient applied by the finishing op)."""
+    from oracle import clip_oracle as O
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, d, ls, str(tmp_path), False, True), nprocs=world,
+             join=True)
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=42)
+    ref = O.closed_form(I.numpy(), T.numpy(), ls)
+    b = n // world
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        assert abs(float(got["loss"]) - ref["loss"]) < 1e-10
         assert O.rel_err(got["dI"], ref["dI"][r * b:(r + 1) * b]) < 1e-10
         assert O.rel_err(got["dT"], ref["dT"][r * b:(r + 1) * b]) < 1e-10
         assert abs(float(got["ds"][0]) - ref["dscale"]) < 1e-10 * max(1.0, abs(ref["dscale"]))
