@@ -140,6 +140,11 @@ int vlpclip_scale_prep(const void* logit_scale, int is_f64, float* scale, float*
 /* out3 = {loss, image_loss, text_loss} from the two (all-reduced) loss sums (:550-552) */
 int vlpclip_loss_finish(const float* sums2, int n_global, float* out3, void* stream);
 
+/* measurement hook: bracket the grad_pair_kernel launches of subsequent vlpclip_grad calls with
+ * CUDA events on their stream (enable = 1) and read the duration of the latest call in ms */
+int vlpclip_time_grad_kernel(int enable);
+float vlpclip_last_grad_kernel_ms(void);
+
 /* host-only: the backward's work partition for n_clusters SM pairs (see grad_bwd.cu, "stream-K").
  * seg rows = {cluster, row block, t0, t1, slot} (slot -1: whole row block, final rows written by the
  * kernel; 0 / 1: partial block of that cluster), red rows = {row block, cluster, slot} in the

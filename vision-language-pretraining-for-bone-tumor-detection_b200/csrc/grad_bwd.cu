@@ -784,6 +784,18 @@ static int n_pairs_of_device() {
   return n > 1 ? n / 2 : 74;   // no device (host-side size queries): assume a B200
 }
 
+// optional CUDA-event bracket around the grad_pair_kernel launches of the next vlpclip_grad calls
+// (bench.py's roofline line: the dominant kernel alone, on the stream it runs on)
+struct KernelTimer {
+  bool enabled = false;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool pending = false;
+};
+static KernelTimer& kernel_timer() {
+  static KernelTimer t;
+  return t;
+}
+
 static int plan_clusters(int n_row_blocks, int total_tiles) {
   const long long total = (long long)n_row_blocks * total_tiles;
   const int n_pairs = n_pairs_of_device();
@@ -920,12 +932,18 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   const int n_pass = p.kblocks > 8 ? 2 : 1;
   const int per_pass = (p.kblocks + n_pass - 1) / n_pass;
   float* ds_keep = p.ds_part;
+  KernelTimer& kt = kernel_timer();
+  if (kt.enabled) VLP_CUDA_OK(cudaEventRecord(kt.e0, stream));
   for (int pass = 0; pass < n_pass; ++pass) {
     p.db0 = pass * per_pass;
     p.ndb = (p.kblocks - p.db0) < per_pass ? (p.kblocks - p.db0) : per_pass;
     p.ds_part = pass == 0 ? ds_keep : nullptr;
     grad_pair_kernel<<<clusters * 2, BWD_THREADS, smem, stream>>>(map_k, map_mn, p);
     VLP_COUNT_LAUNCH(1);
+  }
+  if (kt.enabled) {
+    VLP_CUDA_OK(cudaEventRecord(kt.e1, stream));
+    kt.pending = true;
   }
   {
     // (a no-op for row blocks swept by a single cluster)
@@ -941,6 +959,28 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
     VLP_CUDA_OK(cudaGetLastError());
   }
   return 0;
+}
+
+int vlpclip_time_grad_kernel(int enable) {
+  KernelTimer& kt = kernel_timer();
+  if (enable && !kt.e0) {
+    VLP_CUDA_OK(cudaEventCreate(&kt.e0));
+    VLP_CUDA_OK(cudaEventCreate(&kt.e1));
+  }
+  kt.enabled = enable != 0;
+  kt.pending = false;
+  return 0;
+}
+
+// duration of the grad_pair_kernel launch(es) of the most recent vlpclip_grad call, in ms
+// (synchronises with that call); negative when nothing was recorded
+float vlpclip_last_grad_kernel_ms(void) {
+  KernelTimer& kt = kernel_timer();
+  if (!kt.pending) return -1.f;
+  if (cudaEventSynchronize(kt.e1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, kt.e0, kt.e1) != cudaSuccess) return -1.f;
+  return ms;
 }
 
 // host-side view of the work partition (tests): seg rows = {cluster, row block, t0, t1, slot},
