@@ -513,8 +513,10 @@ class _FusedClipLoss(torch.autograd.Function):
     """loss, image_loss, text_loss = CLIP loss of (I, T, logit_scale); grads by tile recompute.
 
     Sharded mode (``group`` given): every rank passes its local rows; negatives are the global
-    batch (all-gather of T, all-gather + merge of the per-column partial statistics, all-reduce of
-    the loss sums; backward: reduce-scatter of dT_all, all-reduce of d logit_scale).
+    batch (gather of T -- fused into the fp16 operand cast over NVLink peer windows, else NCCL --,
+    all-gather + merge of the per-column partial statistics, all-reduce of the loss sums; backward:
+    reduce-scatter of dT fused into the kernel epilogue over the same windows, else NCCL;
+    all-reduce of d logit_scale).
     """
 
     @staticmethod
@@ -630,13 +632,13 @@ class _FusedClipLoss(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------
-# CUDA-graph variant: forward AND backward of the head captured as one graph
+# CUDA-graph variant: the forward half and the backward half of the head captured as two graphs
 # ----------------------------------------------------------------------------------------------
-# A sharded step at 8 GPUs is ~45 short launches + 7 collectives for ~0.7 ms of tensor work: the host
-# cannot enqueue that fast.  With the temperature on the device nothing in the step needs the host,
-# so the whole fwd+bwd (kernels, NCCL collectives, the side-stream reduce-scatter) is captured once
-# per (shape, dtype, group) and replayed; the gradients are produced at forward time and handed to
-# autograd in backward (multiplied by the upstream gradient).
+# A sharded step at 8 GPUs is ~40 short launches + a handful of collectives for ~0.6 ms of tensor work:
+# the host cannot enqueue that fast.  With the temperature on the device nothing in the step needs the
+# host, so each half (kernels, NCCL collectives, NVLink peer stores) is captured once per
+# (shape, dtypes, group) and replayed; the upstream gradient is a static device scalar that the
+# backward half folds into its kernel epilogues.
 _GRAPH_MODE = os.environ.get("VLP_B200_CUDA_GRAPH", "auto")   # "auto" | "1" | "0"
 _GRAPHS = {}
 GRAPH_REPLAYED_LAUNCHES = 0    # kernels of this library launched through graph replays
