@@ -31,6 +31,15 @@ backward  dT rows stored into the owner's peer window from the kernel epilogue (
     loss_finish(sums, n_global) -> (loss, image_loss, text_loss) 3-vector                  [optional]
     grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale) -> (dx, ds)
     to_backward_operand(x) -> operand copy used by grad (fp16 on the GPU)
+  optional, fused with their collectives over peer windows (NVLink on the GPU; emulated with gloo
+  collectives by ``tests/kernel_contract_ops.WindowContractOps``):
+    push_gather(i_loc, t_loc, group, world, rank) -> (i_operand, t_all_operand) | None
+        gathers the text shard in the backward's operand format; ends with a collective all ranks pass
+    peer_window(group, world, rank, rows, d, device) -> window | None
+    grad_scatter(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
+                 window) -> (parity, ds)      rows of dX stored into slot `rank` of their owner's window
+    scatter_finish(window, parity, out_mul, out_dtype, device) -> dX rows owned by this rank
+        (sum of the slots in rank order, times out_mul); call after a collective all ranks pass
 """
 from __future__ import annotations
 
