@@ -9,14 +9,18 @@
 // S tile and the accumulator cannot share an SM at d = 512. The kernel therefore runs on CTA PAIRS
 // (cluster of 2, one CTA per SM):
 //   rank 0 "producer":  S tile = X Y_t^T with X resident in TMEM (TS form), 8 softmax warps turn
-//                       it into the fp16 tile G*2^13 (two ex2 per logit), staged in local smem
-//                       (K-major, 128B swizzle) and pushed to the peer with one
-//                       cp.async.bulk shared::cta -> shared::cluster (18 B/cycle measured).
-//   rank 1 "consumer":  dX block [128 x d] fp32 stays in TMEM for the whole sweep;
+//                       it into the fp16 tile G*2^13 (one ex2 per logit on the fast path, two on
+//                       the guarded fallback), staged in local smem (K-major, 128B swizzle) and
+//                       pushed to the peer with one cp.async.bulk shared::cta -> shared::cluster
+//                       (18 B/cycle measured).
+//   rank 1 "consumer":  dX block [128 x d] fp32 stays in TMEM for a whole segment of the sweep;
 //                       acc += G_tile (A, smem, K-major) * Y_t (B, smem, MN-major), N = 256 per
 //                       instruction; slot release back to the producer by a multicast
-//                       tcgen05.commit. Epilogue scales and stores (or red.adds when the column
-//                       range is split across clusters).
+//                       tcgen05.commit. The epilogue scales and stores full 128-byte lines:
+//                       final rows (to dX, or straight into the owning rank's NVLink peer window
+//                       for the fused reduce-scatter) when the segment covers its row block, else
+//                       the pair's partial slot, summed later in fixed order.
+// Work is cut "stream-K" style: every SM pair sweeps the same number of tiles (see WorkRange).
 // Neither S nor G ever leaves the SM pair.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
