@@ -45,6 +45,7 @@ _SIGNATURES = {
                              c_size_t, c_void_p]),
     "vlpclip_time_grad_kernel": (c_int, [c_int]),
     "vlpclip_last_grad_kernel_ms": (c_float, []),
+    "vlpclip_dev_set_wait_profile": (c_int, [c_void_p]),
     "vlpclip_grad_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                   c_void_p]),
     "vlpclip_grad_scatter": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

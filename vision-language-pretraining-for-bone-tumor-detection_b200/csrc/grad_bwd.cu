@@ -76,6 +76,7 @@ struct GradParams {
   float* part;          // [n_clusters][2][128, d] fp32 partial blocks of row blocks that are split
                         // between clusters (slot 0: head segment, slot 1: tail segment)
   float* ds_part;       // [n_clusters * 8] or nullptr
+  long long* wait_prof; // [n_clusters][16] blocked-cycle counters (VLP_PROFILE_WAITS builds only)
   RowScatter scatter;   // optional: final rows go to per-owner buffers (fused reduce-scatter)
 };
 
@@ -155,6 +156,18 @@ __device__ __forceinline__ size_t scatter_row(const RowScatter& sc, int row, uin
   base = reinterpret_cast<uint8_t*>(sc.base[o]);
   return (size_t)(row - o * sc.rows_per_owner);
 }
+
+// -DVLP_PROFILE_WAITS: cycles each role spends blocked on each barrier (dev tool, tools/wait_profile.py)
+#ifdef VLP_PROFILE_WAITS
+#define VLP_WAIT(idx, stmt)                  \
+  do {                                       \
+    const long long t0__ = clock64();        \
+    stmt;                                    \
+    wait_cyc[idx] += clock64() - t0__;       \
+  } while (0)
+#else
+#define VLP_WAIT(idx, stmt) stmt
+#endif
 
 struct BwdBarriers {
   uint64_t full[P_STAGES];
@@ -255,6 +268,10 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
+#ifdef VLP_PROFILE_WAITS
+  long long wait_cyc[16] = {0};
+  const long long kernel_t0 = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P_STAGES; ++i) {
@@ -302,7 +319,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
             const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
             const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
-            mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+            VLP_WAIT(0, mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1));
             if (elect_one()) {
               mbar_expect_tx(smem_u32(&bars->full[st]), nkb * P_BOX_BYTES);
               for (int q = 0; q < nkb; ++q)
@@ -319,18 +336,18 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
       Segment sg;
       for (; work.next(sg); ++item_ctr) {
         const int t0 = sg.t0, t1 = sg.t1;
-        mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+        VLP_WAIT(1, mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1));
         tc_fence_after();
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
           const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
           const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-          mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1);
+          VLP_WAIT(2, mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1));
           tc_fence_after();
           const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
           for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
             const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
             const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
-            mbar_wait(smem_u32(&bars->full[st]), ph);
+            VLP_WAIT(3, mbar_wait(smem_u32(&bars->full[st]), ph));
             tc_fence_after();
             if (elect_one()) {
               for (int q = 0; q < nkb; ++q) {
@@ -369,7 +386,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         const int row = rb * 128 + row_in_blk;
         const bool row_ok = row < p.n_rows;
         if (item_ctr > 0) {
-          mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+          VLP_WAIT(4, mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1));
           tc_fence_after();
         }
         {
@@ -405,7 +422,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
           const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
           const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-          mbar_wait(smem_u32(&bars->s_full[buf]), use & 1);
+          VLP_WAIT(5, mbar_wait(smem_u32(&bars->s_full[buf]), use & 1));
           tc_fence_after();
           uint32_t v[64];
           {
@@ -449,7 +466,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           // stage the fp16 G tile (K-major, 128B swizzle) and push it to the consumer CTA
           const uint32_t slot = tile_ctr & 1;
           if (tile_ctr >= 2)
-            mbar_wait_cluster(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1);
+            VLP_WAIT(6, mbar_wait_cluster(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
           const uint32_t dst = gslots + slot * G_SLOT_BYTES + half * 16384 + row_in_blk * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -459,7 +476,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
                          : "memory");
           }
           fence_proxy_async_smem();
-          bar_sync(1, 256);
+          VLP_WAIT(7, bar_sync(1, 256));
           if (warp == 2 && lane == 0) {
             const uint32_t rbar = mapa_shared(smem_u32(&bars->g_full[slot]), 1);
             const uint32_t rdst = mapa_shared(gslots + slot * G_SLOT_BYTES, 1);
@@ -503,7 +520,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
             const int nb = min(4, p.ndb - nc * 4);
             for (int kh = 0; kh < 2; ++kh, ++it) {
               const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
-              mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+              VLP_WAIT(8, mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1));
               if (elect_one()) {
                 mbar_expect_tx(smem_u32(&bars->full[st]), nb * 8192);
                 for (int b = 0; b < nb; ++b)
@@ -522,12 +539,12 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
       for (; work.next(sg); ++item_ctr) {
         const int t0 = sg.t0, t1 = sg.t1;
         if (item_ctr > 0) {
-          mbar_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1);
+          VLP_WAIT(9, mbar_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1));
           tc_fence_after();
         }
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
           const uint32_t slot = tile_ctr & 1;
-          mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1);
+          VLP_WAIT(10, mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
           tc_fence_after();
           const uint32_t ga = gslots + slot * G_SLOT_BYTES;
           for (int nc = 0; nc < n_nc; ++nc) {
@@ -535,7 +552,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
             const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
             for (int kh = 0; kh < 2; ++kh, ++it) {
               const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
-              mbar_wait(smem_u32(&bars->full[st]), ph);
+              VLP_WAIT(11, mbar_wait(smem_u32(&bars->full[st]), ph));
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t sb = ring + st * C_STAGE_BYTES;
@@ -639,6 +656,17 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     }
   }
 
+#ifdef VLP_PROFILE_WAITS
+  if (p.wait_prof != nullptr && lane == 0) {
+    long long* o = p.wait_prof + (size_t)cluster_id * 16;
+    // one representative warp per role writes its counters (indices are disjoint between roles)
+    const bool rep = (rank == 0) ? (warp <= 2) : (warp <= 2);
+    if (rep)
+      for (int i = 0; i < 12; ++i)
+        if (wait_cyc[i] != 0) o[i] = wait_cyc[i];
+    if (warp == 0) o[12 + rank] = clock64() - kernel_t0;
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -800,6 +828,11 @@ static KernelTimer& kernel_timer() {
   return t;
 }
 
+static long long*& wait_prof_buffer() {
+  static long long* p = nullptr;
+  return p;
+}
+
 static int plan_clusters(int n_row_blocks, int total_tiles) {
   const long long total = (long long)n_row_blocks * total_tiles;
   const int n_pairs = n_pairs_of_device();
@@ -894,6 +927,7 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   p.dx_bf16 = dx_bf16;
   p.out_mul = out_mul;
   if (scatter) p.scatter = *scatter;
+  p.wait_prof = wait_prof_buffer();
   p.xmax = xmax;
   p.xlg = xlg;
   p.ymax = ymax;
@@ -962,6 +996,12 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
   }
+  return 0;
+}
+
+// dev builds (-DVLP_PROFILE_WAITS): device buffer of 74 x 16 int64 the next grad kernels fill
+int vlpclip_dev_set_wait_profile(void* buf) {
+  wait_prof_buffer() = (long long*)buf;
   return 0;
 }
 
