@@ -29,7 +29,10 @@
 
 namespace vlp {
 
-constexpr int BWD_THREADS = 320;
+constexpr int SMX_GROUPS = 2;                      // column groups of the S tile: 4 softmax warps each (4 groups measured 3 % slower)
+constexpr int SMX_COLS = 128 / SMX_GROUPS;         // logits per thread per tile
+constexpr int SMX_WARPS = 4 * SMX_GROUPS;
+constexpr int BWD_THREADS = 64 + 32 * SMX_WARPS;   // TMA warp + MMA warp + softmax warps
 constexpr int P_KB_PER_STAGE = 2;           // producer ring stage: 2 boxes of [128 q x 64 k] fp16
 constexpr int P_BOX_BYTES = 16384;
 constexpr int P_STAGE_BYTES = P_KB_PER_STAGE * P_BOX_BYTES;
@@ -75,7 +78,7 @@ struct GradParams {
   const float* out_mul; // optional device scalar multiplied into the output (upstream gradient)
   float* part;          // [n_clusters][2][128, d] fp32 partial blocks of row blocks that are split
                         // between clusters (slot 0: head segment, slot 1: tail segment)
-  float* ds_part;       // [n_clusters * 8] or nullptr
+  float* ds_part;       // [n_clusters * SMX_WARPS] or nullptr
   long long* wait_prof; // [n_clusters][16] blocked-cycle counters (VLP_PROFILE_WAITS builds only)
   RowScatter scatter;   // optional: final rows go to per-owner buffers (fused reduce-scatter)
 };
@@ -192,13 +195,13 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 // P_row = 2^(k (s - xmax_i) - xlg_i),  P_col = 2^(k (s - ymax_j) - ylg_j): subtracting the raw
 // maxima first keeps probabilities near 1 (dominant positive pair) accurate to ~1e-7.
 template <bool kDiag>
-__device__ __forceinline__ void softmax_tile(const uint32_t (&v)[64],
+__device__ __forceinline__ void softmax_tile(const uint32_t (&v)[SMX_COLS],
                                              const float4* __restrict__ ymax4,
                                              const float4* __restrict__ ylg4, float xmax, float xlg,
                                              float scale_log2, float diag_val, int diag_j,
-                                             uint32_t (&out)[32], float& ds_acc) {
+                                             uint32_t (&out)[SMX_COLS / 2], float& ds_acc) {
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
+  for (int q = 0; q < SMX_COLS / 4; ++q) {
     const float4 ym = __ldg(ymax4 + q);
     const float4 yl = __ldg(ylg4 + q);
     const float ymv[4] = {ym.x, ym.y, ym.z, ym.w};
@@ -226,13 +229,13 @@ __device__ __forceinline__ void softmax_tile(const uint32_t (&v)[64],
 // exponent range; the prep kernel checks the global spread and sets fast_flag accordingly.
 // Halves the MUFU work, which bounds this kernel (16 ex2 / clk / SM).
 template <bool kDiag>
-__device__ __forceinline__ void softmax_tile_fast(const uint32_t (&v)[64],
+__device__ __forceinline__ void softmax_tile_fast(const uint32_t (&v)[SMX_COLS],
                                                   const float4* __restrict__ yc4, float xmax,
                                                   float xlg13, float xr, float scale_log2,
                                                   float diag_val_scaled, int diag_j,
-                                                  uint32_t (&out)[32], float& ds_acc) {
+                                                  uint32_t (&out)[SMX_COLS / 2], float& ds_acc) {
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
+  for (int q = 0; q < SMX_COLS / 4; ++q) {
     const float4 yc = __ldg(yc4 + q);
     const float ycv[4] = {yc.x, yc.y, yc.z, yc.w};
     float g[4];
@@ -280,7 +283,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->s_empty[i]), 8);
+      mbar_init(smem_u32(&bars->s_empty[i]), SMX_WARPS);
       mbar_init(smem_u32(&bars->g_full[i]), 1);
       mbar_init(smem_u32(&bars->g_empty[i]), 1);
     }
@@ -371,7 +374,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     } else {
       // ---- softmax warps ----
       const uint32_t quarter = warp & 3;
-      const uint32_t half = (warp - 2) >> 2;
+      const uint32_t grp = (warp - 2) >> 2;          // column group of the S tile
       const uint32_t row_in_blk = quarter * 32 + lane;
       const uint32_t lane_addr = (quarter * 32u) << 16;
       const int dp = p.kblocks * 64;
@@ -389,8 +392,8 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           VLP_WAIT(4, mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1));
           tc_fence_after();
         }
-        {
-          const int k_begin = half * (dp / 2);
+        if (grp < 2) {   // the first 8 warps stage the X block (two K halves) into TMEM
+          const int k_begin = grp * (dp / 2);
           const uint4* src =
               reinterpret_cast<const uint4*>(p.x + (size_t)(row_ok ? row : 0) * p.ldx);
           for (int c0 = 0; c0 < dp / 4; c0 += 16) {
@@ -424,25 +427,24 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
           VLP_WAIT(5, mbar_wait(smem_u32(&bars->s_full[buf]), use & 1));
           tc_fence_after();
-          uint32_t v[64];
+          uint32_t v[SMX_COLS];
           {
-            uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-            const uint32_t a = tmem + lane_addr + tmem_s_col + buf * 128 + half * 64;
-            tmem_ld_x32(a, v0);
-            tmem_ld_x32(a + 32, v1);
+            const uint32_t a = tmem + lane_addr + tmem_s_col + buf * 128 + grp * SMX_COLS;
+#pragma unroll
+            for (int h = 0; h < SMX_COLS / 32; ++h)
+              tmem_ld_x32(a + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * h]));
             tmem_ld_wait();
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
 
-          const int col0 = t * 128 + half * 64;
+          const int col0 = t * 128 + grp * SMX_COLS;
           const float4* ymax4 = reinterpret_cast<const float4*>(p.ymax + col0);
           const float4* ylg4 = reinterpret_cast<const float4*>(p.ylg + col0);
-          uint32_t out[32];
+          uint32_t out[SMX_COLS / 2];
           const int diag_j = dcol - col0;
-          const bool has_diag = diag_j >= 0 && diag_j < 64;
+          const bool has_diag = diag_j >= 0 && diag_j < SMX_COLS;
           const bool any_diag = __any_sync(0xffffffffu, has_diag);
           float diag_val = 0.f;
           if (has_diag) diag_val = -(p.w_row * p.xq[row] + p.w_col * p.yq[dcol]);
@@ -467,16 +469,20 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           const uint32_t slot = tile_ctr & 1;
           if (tile_ctr >= 2)
             VLP_WAIT(6, mbar_wait_cluster(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
-          const uint32_t dst = gslots + slot * G_SLOT_BYTES + half * 16384 + row_in_blk * 128;
+          // (the tile is two [128 rows x 64 logits] K-major blocks of 16 KB; 16-byte chunks of a
+          // row are XOR-swizzled with the row index)
+          const uint32_t dst = gslots + slot * G_SLOT_BYTES + ((grp * SMX_COLS) >> 6) * 16384 +
+                               row_in_blk * 128;
+          const uint32_t cb = ((grp * SMX_COLS) & 63) >> 3;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t a = dst + ((c ^ sw) << 4);
+          for (int c = 0; c < SMX_COLS / 8; ++c) {
+            const uint32_t a = dst + (((cb + c) ^ sw) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(out[c * 4 + 0]),
                          "r"(out[c * 4 + 1]), "r"(out[c * 4 + 2]), "r"(out[c * 4 + 3])
                          : "memory");
           }
           fence_proxy_async_smem();
-          VLP_WAIT(7, bar_sync(1, 256));
+          VLP_WAIT(7, bar_sync(1, 32 * SMX_WARPS));
           if (warp == 2 && lane == 0) {
             const uint32_t rbar = mapa_shared(smem_u32(&bars->g_full[slot]), 1);
             const uint32_t rdst = mapa_shared(gslots + slot * G_SLOT_BYTES, 1);
@@ -497,7 +503,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         ds_total += (double)ds_acc;
       }
       if (p.ds_part != nullptr && lane == 0)
-        p.ds_part[(size_t)cluster_id * 8 + (warp - 2)] = (float)ds_total;
+        p.ds_part[(size_t)cluster_id * SMX_WARPS + (warp - 2)] = (float)ds_total;
       // drain: the consumer must have released every slot we pushed before we may exit
       for (uint32_t back = 0; back < 2 && back < tile_ctr; ++back) {
         const uint32_t tc = tile_ctr - 1 - back;
@@ -843,7 +849,7 @@ static size_t grad_ws_bytes(int n_rows, int n_cols, int d) {
   const size_t nrb = (n_rows + 127) / 128, nt = (n_cols + 127) / 128;
   const size_t max_pairs = 74;   // sized for a whole B200 whatever the current SM limit
   const size_t partials = align256(max_pairs * 2 * 128 * (size_t)d * 4);
-  return 3 * align256(nrb * 128 * 4) + 3 * align256(nt * 128 * 4) + align256(max_pairs * 8 * 4) +
+  return 3 * align256(nrb * 128 * 4) + 3 * align256(nt * 128 * 4) + align256(max_pairs * SMX_WARPS * 4) +
          partials + 1024;
 }
 
@@ -920,7 +926,7 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   int* fast_flag = (int*)(ws + 256);
   ws += 512;
   float* ds_part = (float*)ws;
-  ws += align256((size_t)74 * 8 * 4);
+  ws += align256((size_t)74 * SMX_WARPS * 4);
   float* dx_part = (float*)ws;
   p.dx = dx;
   p.part = dx_part;
@@ -991,7 +997,7 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
     VLP_CUDA_OK(cudaGetLastError());
   }
   if (dscale) {
-    ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, clusters * 8, 1.0f / (2.0f * (float)n_global),
+    ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, clusters * SMX_WARPS, 1.0f / (2.0f * (float)n_global),
                                             dscale);
   VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
