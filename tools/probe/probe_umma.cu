@@ -7,6 +7,8 @@
 // and measures
 //   * tcgen05.mma issue rate per shape (all SMs busy, power-limited clocks)
 //   * L2 -> smem TMA bandwidth per SM with every SM streaming
+//   * the MMA rate under background TMA traffic into the same SM's shared memory ("b" tests:
+//     does the 128 B/cycle of smem co-limit the SS/TS forms, and by how much does cta_group::2 help)
 // Output: one line per test on stdout (PASS/FAIL + numbers).
 #include <cstdio>
 #include <cstdlib>
@@ -558,6 +560,204 @@ static void run_rate(const char* name, RateCfg cfg, int nsm) {
 }
 
 // ---------------------------------------------------------------------------
+// MMA rate UNDER background shared-memory traffic: the same issue loop as rate_kernel while warp 2
+// streams TMA boxes (16 KB each, L2-resident source) into a scratch ring of the same SM, throttled
+// to one box per `bg_interval` cycles (0 = as fast as completions allow).  Tests the round-1
+// hypothesis that the backward's consumer SM (SS N=256: 70 B/cycle of operand reads + 47 B/cycle of
+// TMA writes + 12 B/cycle of peer pushes) is limited by the 128 B/cycle of shared memory, and how
+// much a cta_group::2 pair (each SM stages/reads half of B) relieves it.
+// ---------------------------------------------------------------------------
+template <int CG>
+__global__ void __launch_bounds__(128, 1)
+rate_bg_kernel(RateCfg cfg, const __grid_constant__ CUtensorMap map, int rows_total,
+               int bg_interval, long long* __restrict__ cycles_out,
+               long long* __restrict__ bg_boxes_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  constexpr int BG_STAGES = 4;
+  __shared__ __align__(8) uint64_t bars[1 + BG_STAGES];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int done_flag;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0;
+  const int Ma = cfg.M / CG, Nb = cfg.N / CG;
+  const int KT = 128;
+  const uint32_t op_bytes = ((Ma * KT * 2 + 1023) & ~1023u) + ((Nb * KT * 2 + 1023) & ~1023u);
+  for (uint32_t i = threadIdx.x; i < op_bytes / 4; i += blockDim.x) {
+    uint32_t h = (i * 2654435761u) ^ (blockIdx.x * 97u);
+    uint32_t lo = 0x3c00u | (h & 0x3ffu), hi = 0x3c00u | ((h >> 10) & 0x3ffu);
+    reinterpret_cast<uint32_t*>(smem)[i] = lo | (hi << 16);
+  }
+  fence_proxy_async_smem();
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sB = sA + ((Ma * KT * 2 + 1023) & ~1023u);
+  const uint32_t ring = sA + op_bytes;
+  const uint32_t bar = smem_u32(&bars[0]);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    for (int i = 0; i < BG_STAGES; ++i) mbar_init(smem_u32(&bars[1 + i]), 1);
+    done_flag = 0;
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<CG>(smem_u32(&tmem_base_s), 512);
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (cfg.a_tmem) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0x3c003c00u + threadIdx.x + j;
+    for (int c = 0; c < 64; c += 8) tmem_st_x8(tmem + 256 + ((warp * 32u) << 16) + c, v);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 2) {
+    // background stream (every CTA of the group runs its own)
+    if (elect_one()) {
+      const int nblk_rows = rows_total / 128;
+      long long boxes = 0;
+      long long next = clock64();
+      int issued = 0, waited = 0;
+      auto issue = [&](int i) {
+        const int st = i % BG_STAGES;
+        const uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 7919u;
+        mbar_expect_tx(smem_u32(&bars[1 + st]), 16384);
+        tma_load_2d(ring + st * 16384, &map, smem_u32(&bars[1 + st]), ((h >> 4) % 8) * 64,
+                    ((h >> 8) % nblk_rows) * 128);
+      };
+      for (; issued < BG_STAGES; ++issued) issue(issued);
+      while (!done_flag) {
+        const int st = waited % BG_STAGES;
+        mbar_wait(smem_u32(&bars[1 + st]), (waited / BG_STAGES) & 1);
+        ++waited;
+        ++boxes;
+        if (bg_interval > 0) {
+          next += bg_interval;
+          while (clock64() < next && !done_flag) {
+          }
+        }
+        issue(issued);
+        ++issued;
+      }
+      for (; waited < issued; ++waited)   // drain: no TMA may be in flight at exit
+        mbar_wait(smem_u32(&bars[1 + waited % BG_STAGES]), (waited / BG_STAGES) & 1);
+      bg_boxes_out[blockIdx.x] = boxes;
+    }
+    __syncwarp();
+  }
+  if (warp == 0 && (CG == 1 || rank == 0)) {
+    if (elect_one()) {
+      const uint32_t idesc =
+          make_idesc(UMMA_BF16, UMMA_BF16, cfg.a_major, cfg.b_major, cfg.M, cfg.N);
+      const uint32_t acc_cols = (CG == 2 && cfg.M == 128) ? cfg.N / 2 : cfg.N;
+      const long long t0 = clock64();
+      for (int it = 0; it < cfg.iters; ++it) {
+        const uint32_t acc = tmem + ((acc_cols <= 128 && (it & 1)) ? acc_cols : 0);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          uint64_t ad, bd;
+          if (cfg.a_major == MAJOR_K)
+            ad = make_sdesc_sw128(sA + (ks / 4) * Ma * 128 + (ks % 4) * 32, 0, 1024);
+          else
+            ad = make_sdesc_sw128(sA + ks * 2048, KT * 128, 1024);
+          if (cfg.b_major == MAJOR_K)
+            bd = make_sdesc_sw128(sB + (ks / 4) * Nb * 128 + (ks % 4) * 32, 0, 1024);
+          else
+            bd = make_sdesc_sw128(sB + ks * 2048, KT * 128, 1024);
+          if (cfg.a_tmem)
+            umma_ts<CG>(acc, tmem + 256 + ks * 8, bd, idesc, 1);
+          else
+            umma_ss<CG>(acc, ad, bd, idesc, 1);
+        }
+      }
+      if (CG == 2)
+        umma_commit_mcast<CG>(bar, 0x3);
+      else
+        umma_commit<CG>(bar);
+      mbar_wait_cluster(bar, 0);
+      const long long t1 = clock64();
+      cycles_out[blockIdx.x / CG] = t1 - t0;
+    }
+    __syncwarp();
+  }
+  mbar_wait_cluster(bar, 0);   // every CTA of the group sees the commit
+  if (threadIdx.x == 0) done_flag = 1;
+  tc_fence_after();
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == 1) tmem_dealloc<CG>(tmem, 512);
+}
+
+static void run_rate_bg(const char* name, RateCfg cfg, int bg_interval, int nsm) {
+  const int Ma = cfg.M / cfg.cta_group, Nb = cfg.N / cfg.cta_group;
+  const size_t smem = (size_t)(Ma + Nb) * 128 * 2 + 4 * 16384 + 6144;
+  const int grid = (nsm / cfg.cta_group) * cfg.cta_group;
+  const int rows_total = 65536;   // 64 MB source: L2 resident
+  uint16_t* d;
+  CK(cudaMalloc(&d, (size_t)rows_total * 512 * 2));
+  CK(cudaMemset(d, 0x11, (size_t)rows_total * 512 * 2));
+  CUtensorMap map = make_map_16b(d, 512, rows_total, 128);
+  long long *dcyc, *dbox;
+  CK(cudaMalloc(&dcyc, grid * sizeof(long long)));
+  CK(cudaMalloc(&dbox, grid * sizeof(long long)));
+  CK(cudaMemset(dcyc, 0, grid * sizeof(long long)));
+  CK(cudaMemset(dbox, 0, grid * sizeof(long long)));
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(128);
+  lc.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cfg.cta_group;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaError_t le;
+    if (cfg.cta_group == 1) {
+      CK(cudaFuncSetAttribute(rate_bg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      le = cudaLaunchKernelEx(&lc, rate_bg_kernel<1>, cfg, map, rows_total, bg_interval, dcyc, dbox);
+    } else {
+      CK(cudaFuncSetAttribute(rate_bg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      le = cudaLaunchKernelEx(&lc, rate_bg_kernel<2>, cfg, map, rows_total, bg_interval, dcyc, dbox);
+    }
+    if (le != cudaSuccess) {
+      printf("RATEBG %-36s LAUNCH-FAIL %s\n", name, cudaGetErrorString(le));
+      cudaGetLastError();
+      return;
+    }
+    cudaError_t se = cudaDeviceSynchronize();
+    if (se != cudaSuccess) {
+      printf("RATEBG %-36s RUNTIME-FAIL %s\n", name, cudaGetErrorString(se));
+      exit(3);
+    }
+  }
+  std::vector<long long> cyc(grid), box(grid);
+  CK(cudaMemcpy(cyc.data(), dcyc, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(box.data(), dbox, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+  double avg = 0, boxes = 0;
+  const int units = grid / cfg.cta_group;
+  for (int i = 0; i < units; ++i) avg += (double)cyc[i];
+  for (int i = 0; i < grid; ++i) boxes += (double)box[i];
+  avg /= units;
+  boxes /= grid;
+  const double n_instr = (double)cfg.iters * 8;
+  const double macs = (double)cfg.M * cfg.N * 16 * n_instr;
+  printf("RATEBG %-36s interval=%4d  cyc/instr=%.1f  MAC/cyc/SM=%.0f  background=%.1f B/cyc/SM\n",
+         name, bg_interval, avg / n_instr, macs / avg / cfg.cta_group, boxes * 16384.0 / avg);
+  cudaFree(d);
+  cudaFree(dcyc);
+  cudaFree(dbox);
+}
+
+// ---------------------------------------------------------------------------
 // L2 -> smem TMA streaming bandwidth
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1)
@@ -821,8 +1021,9 @@ int main(int argc, char** argv) {
   printf("device %s sm_%d%d SMs=%d smem/block optin=%zu\n", prop.name, prop.major, prop.minor,
          prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
   const int nsm = prop.multiProcessorCount;
-  bool do_tiles = true, do_rate = true, do_l2 = true, do_ds = true;
+  bool do_tiles = true, do_rate = true, do_l2 = true, do_ds = true, do_bg = true;
   if (argc > 1) {
+    do_bg = strstr(argv[1], "b") != nullptr;
     do_tiles = strstr(argv[1], "t") != nullptr;
     do_rate = strstr(argv[1], "r") != nullptr;
     do_l2 = strstr(argv[1], "l") != nullptr;
@@ -868,6 +1069,16 @@ int main(int argc, char** argv) {
     run_rate("cg2_M128_N256_SS_KK",        {2, 128, 256, 0, 0, 0, it}, nsm);
     run_rate("cg2_M128_N256_SS_K_MN",      {2, 128, 256, 0, 0, 1, it}, nsm);
     run_rate("cg2_M256_N256_TS_MN",        {2, 256, 256, 1, 0, 1, it}, nsm);
+  }
+  if (do_bg) {
+    const int it = 1000;
+    // interval 350 = one 16 KB box per 350 cycles = 47 B/cycle (the consumer's Y stream), 700 = half
+    for (int iv : {0, 350, 700, 100000000}) {
+      run_rate_bg("cg1_M128_N256_SS_K_MN", {1, 128, 256, 0, 0, 1, it}, iv, nsm);
+      run_rate_bg("cg2_M256_N256_SS_K_MN", {2, 256, 256, 0, 0, 1, it}, iv, nsm);
+      run_rate_bg("cg1_M128_N128_TS_K", {1, 128, 128, 1, 0, 0, it}, iv, nsm);
+      run_rate_bg("cg2_M256_N128_TS_K", {2, 256, 128, 1, 0, 0, it}, iv, nsm);
+    }
   }
   if (do_l2) {
     run_l2bw("rows8192_distinct", 8192, 0, nsm);     // 8 MB footprint
