@@ -145,8 +145,9 @@ int vlpclip_loss_finish(const float* sums2, int n_global, float* out3, void* str
 int vlpclip_time_grad_kernel(int enable);
 float vlpclip_last_grad_kernel_ms(void);
 /* development builds only (-DVLP_PROFILE_WAITS, tools/wait_profile.py): device buffer of
- * [n_sm_pairs][16] int64 in which the next backward kernels record, per role, the cycles spent
- * blocked on each pipeline barrier; a no-op in the shipped library */
+ * [74 SM pairs][16] int64 (backward kernel) followed by [148 SMs][8] int64 (forward kernel) in which
+ * the next kernels record, per role, the cycles spent blocked on each pipeline barrier; a no-op in
+ * the shipped library */
 int vlpclip_dev_set_wait_profile(void* buf);
 
 /* host-only: the backward's work partition for n_clusters SM pairs (see grad_bwd.cu, "stream-K").

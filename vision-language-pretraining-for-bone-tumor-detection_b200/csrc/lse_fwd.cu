@@ -29,6 +29,19 @@ constexpr int FWD_SMW = 16;                  // softmax warps: 4 TMEM lane quart
 constexpr int FWD_CG = FWD_SMW / 4;          // column groups per tile
 constexpr int FWD_CPT = 128 / FWD_CG;        // columns per thread (32)
 constexpr int FWD_THREADS = 64 + FWD_SMW * 32;
+// experiment switches of tools/pipeline_experiments.py (never set in the shipped library):
+// VLP_EXP_HALF_Y_F  timing mock, the TMA warp fetches half of the boxes of each ring stage
+// VLP_EXP_NO_SMX_F  timing mock, softmax warps only drain the S buffer
+#ifdef VLP_EXP_HALF_Y_F
+constexpr int kFwdBoxDiv = 2;
+#else
+constexpr int kFwdBoxDiv = 1;
+#endif
+#ifdef VLP_EXP_NO_SMX_F
+constexpr bool kFwdNoSoftmax = true;
+#else
+constexpr bool kFwdNoSoftmax = false;
+#endif
 constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: d/2 columns (256 at d = 512, 384 at d = 768)
 // S buffers of 128 columns sit at the top of TMEM: two (double buffered) while d <= 512, a single
 // one for 512 < d <= 768 (MMA and softmax of consecutive tiles then serialise)
@@ -52,6 +65,7 @@ struct LseParams {
   // sum_i exp2(k c_ij - ref) with a log2-domain reference `ref`; the positive pair is left out
   float* col_ref;       // [n_row_blocks][total_tiles * 128]
   float* col_l;         // [n_row_blocks][total_tiles * 128]
+  long long* wait_prof; // [n_sm][8] blocked-cycle counters (VLP_PROFILE_WAITS builds only)
 };
 
 struct FwdBarriers {
@@ -80,6 +94,10 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
   const uint32_t ring = smem_u32(smem);
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
+#ifdef VLP_PROFILE_WAITS
+  long long wait_cyc[8] = {0};
+  const long long kernel_t0 = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < FWD_STAGES; ++i) {
@@ -118,10 +136,11 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           const uint32_t st = it % FWD_STAGES;
           const uint32_t ph = (it / FWD_STAGES) & 1;
           const int nkb = min(FWD_KB_PER_STAGE, p.kblocks - kb);
-          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+          const int nld = (nkb + kFwdBoxDiv - 1) / kFwdBoxDiv;   // = nkb outside the timing mock
+          VLP_WAIT(0, mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1));
           if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bars->full[st]), nkb * FWD_BOX_BYTES);
-            for (int q = 0; q < nkb; ++q)
+            mbar_expect_tx(smem_u32(&bars->full[st]), nld * FWD_BOX_BYTES);
+            for (int q = 0; q < nld; ++q)
               tma_load_2d(ring + st * FWD_STAGE_BYTES + q * FWD_BOX_BYTES, &map_y,
                           smem_u32(&bars->full[st]), (kb + q) * 64, t * 128);
           }
@@ -138,19 +157,19 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       const int chunk = item / p.n_row_blocks;
       const int t0 = chunk * p.tiles_per_chunk;
       const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-      mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+      VLP_WAIT(1, mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1));
       tc_fence_after();
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
         const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-        mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1);
+        VLP_WAIT(2, mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
         for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE, ++it) {
           const uint32_t st = it % FWD_STAGES;
           const uint32_t ph = (it / FWD_STAGES) & 1;
           const int nkb = min(FWD_KB_PER_STAGE, p.kblocks - kb);
-          mbar_wait(smem_u32(&bars->full[st]), ph);
+          VLP_WAIT(3, mbar_wait(smem_u32(&bars->full[st]), ph));
           tc_fence_after();
           if (elect_one()) {
             for (int q = 0; q < nkb; ++q) {
@@ -193,7 +212,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
 
       // ---- stage the X row block into TMEM (bf16 pairs packed per 32-bit column) ----
       if (item_ctr > 0) {
-        mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+        VLP_WAIT(4, mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1));
         tc_fence_after();
       }
       {
@@ -225,7 +244,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
         const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-        mbar_wait(smem_u32(&bars->s_full[buf]), use & 1);
+        VLP_WAIT(5, mbar_wait(smem_u32(&bars->s_full[buf]), use & 1));
         tc_fence_after();
         uint32_t v[FWD_CPT];
         tmem_ld_x32(tmem + lane_addr + tmem_s_col + buf * 128 + cg * FWD_CPT, v);
@@ -233,6 +252,10 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
+        if (kFwdNoSoftmax) {   // timing mock: keep the loads observable, skip the arithmetic
+          mraw_run = fmaxf(mraw_run, __uint_as_float(v[lane & (FWD_CPT - 1)]));
+          continue;
+        }
 
         const int col0 = t * 128 + cg * FWD_CPT;
         // columns past n_cols were zero-filled by TMA: mask them out of the statistics
@@ -303,7 +326,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           const uint32_t par = tile_ctr & 1;
           bars->col_s[par][wslot][lane] = c[0];
           if (lane == 0) bars->col_r[par][wslot] = R - COL_HEADROOM;
-          bar_sync(2, FWD_SMW * 32);
+          VLP_WAIT(6, bar_sync(2, FWD_SMW * 32));
           const uint32_t st = wslot * 32 + lane;   // the first 128 softmax threads own one column
           if (st < 128) {
             const uint32_t g = st >> 5, cc = st & 31;   // warps of column group g: slots g*4 .. g*4+3
@@ -332,6 +355,14 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     }
   }
 
+#ifdef VLP_PROFILE_WAITS
+  if (p.wait_prof != nullptr && lane == 0 && warp <= 2) {
+    long long* o = p.wait_prof + (size_t)blockIdx.x * 8;   // indices are disjoint between roles
+    for (int i = 0; i < 7; ++i)
+      if (wait_cyc[i] != 0) o[i] = wait_cyc[i];
+    if (warp == 0) o[7] = clock64() - kernel_t0;
+  }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
@@ -611,6 +642,7 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   pick_chunks(p.n_row_blocks, p.total_tiles, nsm, &p.n_chunks, &p.tiles_per_chunk);
   p.diag_shift = diag_shift;
   p.scale_ptr = scale;
+  p.wait_prof = wait_prof_buffer() ? wait_prof_buffer() + WAIT_PROF_BWD_WORDS : nullptr;
   const int nparts = p.n_chunks * FWD_CG;
   p.part_m = (float*)workspace;
   p.part_l = p.part_m + (size_t)nparts * n_rows;
