@@ -32,6 +32,10 @@ VARIANTS = {
     "half_y_bwd_p": ("mock", ["VLP_EXP_HALF_Y_P"], "backward producer streams half of Y"),
     "half_y_bwd_c": ("mock", ["VLP_EXP_HALF_Y_C"], "backward consumer streams half of Y"),
     "half_y_bwd_pc": ("mock", ["VLP_EXP_HALF_Y_P", "VLP_EXP_HALF_Y_C"], "both backward roles stream half of Y"),
+    "fine_rings": ("real", ["VLP_P_KB_PER_STAGE=1", "VLP_C_Q_PER_STAGE=32", "VLP_FWD_KB_PER_STAGE=1"],
+                   "16 KB ring stages everywhere (8 / 8 / 12 stages): fewer bytes pinned under the MMAs"),
+    "fine_rings_pingpong": ("real", ["VLP_P_KB_PER_STAGE=1", "VLP_C_Q_PER_STAGE=32", "VLP_FWD_KB_PER_STAGE=1",
+                                     "VLP_BWD_PINGPONG"], "both real variants together"),
     "no_smx": ("mock", ["VLP_EXP_NO_SMX", "VLP_EXP_NO_SMX_F"], "softmax arithmetic removed (fwd + bwd)"),
     "bwd_decouple": ("mock", ["VLP_EXP_DECOUPLE"], "no G hand-off: each backward role at its own pace"),
     "bwd_decouple_half_y": ("mock", ["VLP_EXP_DECOUPLE", "VLP_EXP_HALF_Y_P", "VLP_EXP_HALF_Y_C"],

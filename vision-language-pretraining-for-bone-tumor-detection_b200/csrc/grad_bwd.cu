@@ -73,13 +73,27 @@ constexpr bool kDecouple = false;
 static_assert(!kPingPong || SMX_GROUPS == 2, "ping-pong: one warp group per S buffer / G slot");
 constexpr int SMX_PASSES = kPingPong ? 2 : 1;                 // SMX_COLS-wide passes per thread and tile
 constexpr int SMX_TILE_WARPS = kPingPong ? 4 : SMX_WARPS;     // warps that share one S tile
-constexpr int P_KB_PER_STAGE = 2;           // producer ring stage: 2 boxes of [128 q x 64 k] fp16
+// ring geometry (overridable for tools/pipeline_experiments.py: finer stages pin fewer bytes under
+// the MMAs that read them, leaving more of the 128 KB ring in flight)
+#ifndef VLP_P_KB_PER_STAGE
+#define VLP_P_KB_PER_STAGE 2
+#endif
+#ifndef VLP_C_Q_PER_STAGE
+#define VLP_C_Q_PER_STAGE 64
+#endif
+constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
+constexpr int P_KB_PER_STAGE = VLP_P_KB_PER_STAGE;   // producer ring stage: boxes of [128 q x 64 k] fp16
 constexpr int P_BOX_BYTES = 16384;
 constexpr int P_STAGE_BYTES = P_KB_PER_STAGE * P_BOX_BYTES;
-constexpr int P_STAGES = 4;
-constexpr int C_STAGES = 4;                 // consumer ring: [64 q x 256 d] fp16 = 32 KB
-constexpr int C_STAGE_BYTES = 32768;
-constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
+constexpr int P_STAGES = RING_BYTES / P_STAGE_BYTES;                // 4 stages of 32 KB
+constexpr int C_Q_PER_STAGE = VLP_C_Q_PER_STAGE;     // consumer ring stage: [64 q x 256 d] fp16 = 32 KB
+constexpr int C_BOX_BYTES = C_Q_PER_STAGE * 128;     // one [q x 64 d] box
+constexpr int C_STAGE_BYTES = 4 * C_BOX_BYTES;
+constexpr int C_STAGES = RING_BYTES / C_STAGE_BYTES;                // 4 stages of 32 KB
+constexpr int C_SPLIT = 128 / C_Q_PER_STAGE;         // stages per (tile, 256-column accumulator chunk)
+constexpr int RING_BARS = P_STAGES > C_STAGES ? P_STAGES : C_STAGES;
+static_assert(P_KB_PER_STAGE == 1 || P_KB_PER_STAGE == 2 || P_KB_PER_STAGE == 4, "producer stage");
+static_assert(C_Q_PER_STAGE == 32 || C_Q_PER_STAGE == 64, "consumer stage");
 constexpr int G_SLOT_BYTES = 32768;         // [128 rows x 128 q] fp16
 constexpr int G_SLOTS = 2;
 constexpr int BAR_BYTES = 1024;               // barrier block
@@ -203,8 +217,8 @@ __device__ __forceinline__ size_t scatter_row(const RowScatter& sc, int row, uin
 // (VLP_WAIT: blocked-cycle accounting of the -DVLP_PROFILE_WAITS dev build, see common.cuh)
 
 struct BwdBarriers {
-  uint64_t full[P_STAGES];
-  uint64_t empty[P_STAGES];
+  uint64_t full[RING_BARS];
+  uint64_t empty[RING_BARS];
   uint64_t s_full[2];
   uint64_t s_empty[2];
   uint64_t x_ready;
@@ -307,7 +321,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
 #endif
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P_STAGES; ++i) {
+    for (int i = 0; i < RING_BARS; ++i) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
@@ -571,16 +585,16 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         for (int t = t0; t < t1; ++t)
           for (int nc = 0; nc < n_nc; ++nc) {
             const int nb = min(4, p.ndb - nc * 4);
-            for (int kh = 0; kh < 2; ++kh, ++it) {
+            for (int kh = 0; kh < C_SPLIT; ++kh, ++it) {
               const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
               VLP_WAIT(8, mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1));
               const int nld = (nb + kConsBoxDiv - 1) / kConsBoxDiv;   // = nb outside the timing mocks
               if (elect_one()) {
-                mbar_expect_tx(smem_u32(&bars->full[st]), nld * 8192);
+                mbar_expect_tx(smem_u32(&bars->full[st]), nld * C_BOX_BYTES);
                 for (int b = 0; b < nld; ++b)
-                  tma_load_2d(ring + st * C_STAGE_BYTES + b * 8192, &map_y_mn,
+                  tma_load_2d(ring + st * C_STAGE_BYTES + b * C_BOX_BYTES, &map_y_mn,
                               smem_u32(&bars->full[st]), (p.db0 + nc * 4 + b) * 64,
-                              t * 128 + kh * 64);
+                              t * 128 + kh * C_Q_PER_STAGE);
               }
               __syncwarp();
             }
@@ -604,16 +618,19 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           for (int nc = 0; nc < n_nc; ++nc) {
             const int nb = min(4, p.ndb - nc * 4);
             const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
-            for (int kh = 0; kh < 2; ++kh, ++it) {
+            for (int kh = 0; kh < C_SPLIT; ++kh, ++it) {
               const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
               VLP_WAIT(11, mbar_wait(smem_u32(&bars->full[st]), ph));
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t sb = ring + st * C_STAGE_BYTES;
+                // G tile = two K-major blocks of [128 rows x 64 q]; stage kh covers q [kh * C_Q, +C_Q)
+                const int q0 = kh * C_Q_PER_STAGE;
+                const uint32_t g0 = ga + (q0 >> 6) * 16384 + ((q0 & 63) >> 4) * 32;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint64_t ad = make_sdesc_sw128(ga + kh * 16384 + i * 32, 0, 1024);
-                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, 8192, 1024);
+                for (int i = 0; i < C_Q_PER_STAGE / 16; ++i) {
+                  const uint64_t ad = make_sdesc_sw128(g0 + i * 32, 0, 1024);
+                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, C_BOX_BYTES, 1024);
                   umma_ss<1>(tmem + nc * 256, ad, bd, idesc, !(t == t0 && kh == 0 && i == 0));
                 }
                 umma_commit<1>(smem_u32(&bars->empty[st]));
@@ -1005,7 +1022,7 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   CUtensorMap map_k, map_mn;
   rc = make_tmap_sw128(&map_k, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
   if (rc) return rc;
-  rc = make_tmap_sw128(&map_mn, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 64);
+  rc = make_tmap_sw128(&map_mn, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, C_Q_PER_STAGE);
   if (rc) return rc;
 
   static_assert(sizeof(BwdBarriers) <= BAR_BYTES, "barrier block");

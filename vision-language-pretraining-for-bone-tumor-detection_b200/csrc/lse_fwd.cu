@@ -21,10 +21,13 @@
 
 namespace vlp {
 
-constexpr int FWD_KB_PER_STAGE = 2;          // k-blocks (128 rows x 64 bf16 = 16 KB boxes) per stage
+#ifndef VLP_FWD_KB_PER_STAGE
+#define VLP_FWD_KB_PER_STAGE 2               // (overridable for tools/pipeline_experiments.py)
+#endif
+constexpr int FWD_KB_PER_STAGE = VLP_FWD_KB_PER_STAGE;   // k-blocks (128 rows x 64 bf16 = 16 KB boxes) per stage
 constexpr int FWD_BOX_BYTES = 128 * 128;
 constexpr int FWD_STAGE_BYTES = FWD_KB_PER_STAGE * FWD_BOX_BYTES;
-constexpr int FWD_STAGES = 6;
+constexpr int FWD_STAGES = 6 * 2 / FWD_KB_PER_STAGE;     // 192 KB ring: 6 stages of 32 KB
 constexpr int FWD_SMW = 16;                  // softmax warps: 4 TMEM lane quarters x 4 column groups
 constexpr int FWD_CG = FWD_SMW / 4;          // column groups per tile
 constexpr int FWD_CPT = 128 / FWD_CG;        // columns per thread (32)
