@@ -28,6 +28,8 @@ VARIANTS = {
     "base": ("real", [], "shipped kernels + wait counters"),
     "bwd_pingpong": ("real", ["VLP_BWD_PINGPONG"],
                      "softmax warp groups alternate whole tiles (2 tile times per tile and group)"),
+    "fwd_pair": ("real", ["VLP_FWD_PAIR"],
+                 "forward on CTA pairs with cta_group::2 MMAs: each SM stages half of every Y tile"),
     "half_y_fwd": ("mock", ["VLP_EXP_HALF_Y_F"], "forward streams half of Y per SM (cta_group::2 traffic)"),
     "half_y_bwd_p": ("mock", ["VLP_EXP_HALF_Y_P"], "backward producer streams half of Y"),
     "half_y_bwd_c": ("mock", ["VLP_EXP_HALF_Y_C"], "backward consumer streams half of Y"),
