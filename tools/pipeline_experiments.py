@@ -1,7 +1,8 @@
 """Which stage bounds the forward / backward pipelines?  One gpurun call answers it.
 
-Builds csrc/*.cu several times with experiment switches (see the comment blocks at the top of
-lse_fwd.cu and grad_bwd.cu) into tools/variants/libvlpclip_<name>.so -- the shipped library is never
+Builds the staged kernel versions csrc/next/{lse_fwd,grad_bwd}.cu (+ csrc/prologue.cu) several times
+with experiment switches (see the comment blocks at the top of those files) into
+tools/variants/libvlpclip_<name>.so -- the shipped library and its sources csrc/*.cu are never
 touched -- and, on a B200, runs every variant in its own process (a hung mock cannot take the
 others down): kernel times of the forward sweep (rows only / fused columns) and of one backward
 pass, plus the blocked-cycle profile of every pipeline role (all variants carry
@@ -25,7 +26,7 @@ from vlp_b200 import _build, _lib  # noqa: E402
 VAR_DIR = os.path.join(ROOT, "tools", "variants")
 # name -> (kind, -D switches, what the number means)
 VARIANTS = {
-    "base": ("real", [], "shipped kernels + wait counters"),
+    "base": ("real", [], "staged kernels without switches (= shipped algorithms) + wait counters"),
     "bwd_pingpong": ("real", ["VLP_BWD_PINGPONG"],
                      "softmax warp groups alternate whole tiles (2 tile times per tile and group)"),
     "fwd_pair": ("real", ["VLP_FWD_PAIR"],
@@ -56,11 +57,17 @@ def lib_of(name):
     return os.path.join(VAR_DIR, f"libvlpclip_{name}.so")
 
 
+def next_sources():
+    nxt = os.path.join(_build.CSRC, "next")
+    return [os.path.join(nxt, "lse_fwd.cu"), os.path.join(nxt, "grad_bwd.cu"),
+            os.path.join(_build.CSRC, "prologue.cu")]
+
+
 def build():
     os.makedirs(VAR_DIR, exist_ok=True)
     for name, (_, defs, _) in VARIANTS.items():
         cmd = [_build._nvcc()] + _build.NVCC_FLAGS + ["-DVLP_PROFILE_WAITS"] + [f"-D{d}" for d in defs] + \
-              ["-o", lib_of(name)] + _build.sources()
+              ["-o", lib_of(name)] + next_sources()
         subprocess.run(cmd, check=True)
         print("built", lib_of(name))
 

@@ -116,27 +116,6 @@ inline unsigned long long& launch_counter() {
 }
 #define VLP_COUNT_LAUNCH(k) (::vlp::launch_counter() += (k))
 
-// -DVLP_PROFILE_WAITS (dev builds, tools/wait_profile.py): cycles a role spends blocked on a barrier
-// are added to wait_cyc[idx]; in the shipped library VLP_WAIT(idx, stmt) is just stmt.
-#ifdef VLP_PROFILE_WAITS
-#define VLP_WAIT(idx, stmt)                  \
-  do {                                       \
-    const long long t0__ = clock64();        \
-    stmt;                                    \
-    wait_cyc[idx] += clock64() - t0__;       \
-  } while (0)
-#else
-#define VLP_WAIT(idx, stmt) stmt
-#endif
-// device buffer the profiled kernels write to: [74 SM pairs][16] int64 (backward) followed by
-// [148 SMs][8] int64 (forward); set with vlpclip_dev_set_wait_profile, null = off
-constexpr int WAIT_PROF_BWD_WORDS = 74 * 16;
-constexpr int WAIT_PROF_FWD_WORDS = 148 * 8;
-inline long long*& wait_prof_buffer() {
-  static long long* p = nullptr;
-  return p;
-}
-
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

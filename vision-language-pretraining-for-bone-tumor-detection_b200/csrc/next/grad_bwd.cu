@@ -24,8 +24,8 @@
 // Neither S nor G ever leaves the SM pair.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
-#include "common.cuh"
-#include "../../include/vlpclip.h"
+#include "pipeline_exp.cuh"
+#include "../../../include/vlpclip.h"
 
 namespace vlp {
 
@@ -33,13 +33,67 @@ constexpr int SMX_GROUPS = 2;                      // column groups of the S til
 constexpr int SMX_COLS = 128 / SMX_GROUPS;         // logits per thread per tile
 constexpr int SMX_WARPS = 4 * SMX_GROUPS;
 constexpr int BWD_THREADS = 64 + 32 * SMX_WARPS;   // TMA warp + MMA warp + softmax warps
-constexpr int P_KB_PER_STAGE = 2;           // producer ring stage: 2 boxes of [128 q x 64 k] fp16
+
+// ---- experiment switches (tools/pipeline_experiments.py builds separate libraries with them; the
+// shipped library is compiled with none of them set) -------------------------------------------
+// VLP_BWD_PINGPONG   real variant: the two softmax warp groups alternate whole S tiles (group g owns
+//                    S buffer g and G slot g, a thread walks all 128 logits of its row in two passes)
+//                    instead of splitting every tile by columns -> a group has two tile times per tile
+// VLP_EXP_HALF_Y_P / VLP_EXP_HALF_Y_C   timing mock: the producer's / consumer's TMA warp fetches only
+//                    half of the boxes of every ring stage (the MMAs read stale bytes): what a
+//                    cta_group::2 kernel would stream per SM.  Results are garbage by construction.
+// VLP_EXP_NO_SMX     timing mock: softmax warps skip the arithmetic (G tile = raw bits of S)
+// VLP_EXP_DECOUPLE   timing mock: no G hand-off (producer does not push, consumer does not wait):
+//                    each role runs at its own pace; read the per-role cycles of the wait profile
+#ifdef VLP_BWD_PINGPONG
+constexpr bool kPingPong = true;
+#else
+constexpr bool kPingPong = false;
+#endif
+#ifdef VLP_EXP_HALF_Y_P
+constexpr int kProdBoxDiv = 2;
+#else
+constexpr int kProdBoxDiv = 1;
+#endif
+#ifdef VLP_EXP_HALF_Y_C
+constexpr int kConsBoxDiv = 2;
+#else
+constexpr int kConsBoxDiv = 1;
+#endif
+#ifdef VLP_EXP_NO_SMX
+constexpr bool kNoSoftmaxMath = true;
+#else
+constexpr bool kNoSoftmaxMath = false;
+#endif
+#ifdef VLP_EXP_DECOUPLE
+constexpr bool kDecouple = true;
+#else
+constexpr bool kDecouple = false;
+#endif
+static_assert(!kPingPong || SMX_GROUPS == 2, "ping-pong: one warp group per S buffer / G slot");
+constexpr int SMX_PASSES = kPingPong ? 2 : 1;                 // SMX_COLS-wide passes per thread and tile
+constexpr int SMX_TILE_WARPS = kPingPong ? 4 : SMX_WARPS;     // warps that share one S tile
+// ring geometry (overridable for tools/pipeline_experiments.py: finer stages pin fewer bytes under
+// the MMAs that read them, leaving more of the 128 KB ring in flight)
+#ifndef VLP_P_KB_PER_STAGE
+#define VLP_P_KB_PER_STAGE 2
+#endif
+#ifndef VLP_C_Q_PER_STAGE
+#define VLP_C_Q_PER_STAGE 64
+#endif
+constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
+constexpr int P_KB_PER_STAGE = VLP_P_KB_PER_STAGE;   // producer ring stage: boxes of [128 q x 64 k] fp16
 constexpr int P_BOX_BYTES = 16384;
 constexpr int P_STAGE_BYTES = P_KB_PER_STAGE * P_BOX_BYTES;
-constexpr int P_STAGES = 4;
-constexpr int C_STAGES = 4;                 // consumer ring: [64 q x 256 d] fp16 = 32 KB
-constexpr int C_STAGE_BYTES = 32768;
-constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
+constexpr int P_STAGES = RING_BYTES / P_STAGE_BYTES;                // 4 stages of 32 KB
+constexpr int C_Q_PER_STAGE = VLP_C_Q_PER_STAGE;     // consumer ring stage: [64 q x 256 d] fp16 = 32 KB
+constexpr int C_BOX_BYTES = C_Q_PER_STAGE * 128;     // one [q x 64 d] box
+constexpr int C_STAGE_BYTES = 4 * C_BOX_BYTES;
+constexpr int C_STAGES = RING_BYTES / C_STAGE_BYTES;                // 4 stages of 32 KB
+constexpr int C_SPLIT = 128 / C_Q_PER_STAGE;         // stages per (tile, 256-column accumulator chunk)
+constexpr int RING_BARS = P_STAGES > C_STAGES ? P_STAGES : C_STAGES;
+static_assert(P_KB_PER_STAGE == 1 || P_KB_PER_STAGE == 2 || P_KB_PER_STAGE == 4, "producer stage");
+static_assert(C_Q_PER_STAGE == 32 || C_Q_PER_STAGE == 64, "consumer stage");
 constexpr int G_SLOT_BYTES = 32768;         // [128 rows x 128 q] fp16
 constexpr int G_SLOTS = 2;
 constexpr int BAR_BYTES = 1024;               // barrier block
@@ -160,21 +214,11 @@ __device__ __forceinline__ size_t scatter_row(const RowScatter& sc, int row, uin
   return (size_t)(row - o * sc.rows_per_owner);
 }
 
-// -DVLP_PROFILE_WAITS: cycles each role spends blocked on each barrier (dev tool, tools/wait_profile.py)
-#ifdef VLP_PROFILE_WAITS
-#define VLP_WAIT(idx, stmt)                  \
-  do {                                       \
-    const long long t0__ = clock64();        \
-    stmt;                                    \
-    wait_cyc[idx] += clock64() - t0__;       \
-  } while (0)
-#else
-#define VLP_WAIT(idx, stmt) stmt
-#endif
+// (VLP_WAIT: blocked-cycle accounting of the -DVLP_PROFILE_WAITS dev build, see pipeline_exp.cuh)
 
 struct BwdBarriers {
-  uint64_t full[P_STAGES];
-  uint64_t empty[P_STAGES];
+  uint64_t full[RING_BARS];
+  uint64_t empty[RING_BARS];
   uint64_t s_full[2];
   uint64_t s_empty[2];
   uint64_t x_ready;
@@ -277,13 +321,13 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
 #endif
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P_STAGES; ++i) {
+    for (int i = 0; i < RING_BARS; ++i) {
       mbar_init(smem_u32(&bars->full[i]), 1);
       mbar_init(smem_u32(&bars->empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->s_empty[i]), SMX_WARPS);
+      mbar_init(smem_u32(&bars->s_empty[i]), SMX_TILE_WARPS);
       mbar_init(smem_u32(&bars->g_full[i]), 1);
       mbar_init(smem_u32(&bars->g_empty[i]), 1);
     }
@@ -322,10 +366,11 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
             const uint32_t st = it % P_STAGES, ph = (it / P_STAGES) & 1;
             const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
+            const int nld = (nkb + kProdBoxDiv - 1) / kProdBoxDiv;   // = nkb outside the timing mocks
             VLP_WAIT(0, mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1));
             if (elect_one()) {
-              mbar_expect_tx(smem_u32(&bars->full[st]), nkb * P_BOX_BYTES);
-              for (int q = 0; q < nkb; ++q)
+              mbar_expect_tx(smem_u32(&bars->full[st]), nld * P_BOX_BYTES);
+              for (int q = 0; q < nld; ++q)
                 tma_load_2d(ring + st * P_STAGE_BYTES + q * P_BOX_BYTES, &map_y_k,
                             smem_u32(&bars->full[st]), (kb + q) * 64, t * 128);
             }
@@ -423,67 +468,80 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         float ds_acc = 0.f;
 
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
+          // ping-pong: group g takes the tiles of parity g (= S buffer g = G slot g)
+          if (kPingPong && (tile_ctr & 1) != grp) continue;
           const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
           const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
           VLP_WAIT(5, mbar_wait(smem_u32(&bars->s_full[buf]), use & 1));
           tc_fence_after();
-          uint32_t v[SMX_COLS];
-          {
-            const uint32_t a = tmem + lane_addr + tmem_s_col + buf * 128 + grp * SMX_COLS;
-#pragma unroll
-            for (int h = 0; h < SMX_COLS / 32; ++h)
-              tmem_ld_x32(a + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * h]));
-            tmem_ld_wait();
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
-
-          const int col0 = t * 128 + grp * SMX_COLS;
-          const float4* ymax4 = reinterpret_cast<const float4*>(p.ymax + col0);
-          const float4* ylg4 = reinterpret_cast<const float4*>(p.ylg + col0);
-          uint32_t out[SMX_COLS / 2];
-          const int diag_j = dcol - col0;
-          const bool has_diag = diag_j >= 0 && diag_j < SMX_COLS;
-          const bool any_diag = __any_sync(0xffffffffu, has_diag);
-          float diag_val = 0.f;
-          if (has_diag) diag_val = -(p.w_row * p.xq[row] + p.w_col * p.yq[dcol]);
-          if (fast) {
-            const float4* yc4 = reinterpret_cast<const float4*>(p.yc + col0);
-            float acc = 0.f;   // carries the 2^13 tile scale
-            if (any_diag)
-              softmax_tile_fast<true>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, diag_val * G_SCALE,
-                                      diag_j, out, acc);
-            else
-              softmax_tile_fast<false>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, 0.f, diag_j, out,
-                                       acc);
-            ds_acc = fmaf(acc, 1.0f / G_SCALE, ds_acc);
-          } else if (any_diag) {
-            softmax_tile<true>(v, ymax4, ylg4, xmax, xlg, scale_log2, diag_val, diag_j, out,
-                               ds_acc);
-          } else {
-            softmax_tile<false>(v, ymax4, ylg4, xmax, xlg, scale_log2, 0.f, diag_j, out, ds_acc);
-          }
-
-          // stage the fp16 G tile (K-major, 128B swizzle) and push it to the consumer CTA
           const uint32_t slot = tile_ctr & 1;
-          if (tile_ctr >= 2)
-            VLP_WAIT(6, mbar_wait_cluster(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
-          // (the tile is two [128 rows x 64 logits] K-major blocks of 16 KB; 16-byte chunks of a
-          // row are XOR-swizzled with the row index)
-          const uint32_t dst = gslots + slot * G_SLOT_BYTES + ((grp * SMX_COLS) >> 6) * 16384 +
-                               row_in_blk * 128;
-          const uint32_t cb = ((grp * SMX_COLS) & 63) >> 3;
+#pragma unroll 1
+          for (int pass = 0; pass < SMX_PASSES; ++pass) {
+            const uint32_t cgrp = kPingPong ? (uint32_t)pass : grp;   // SMX_COLS-wide column group
+            uint32_t v[SMX_COLS];
+            {
+              const uint32_t a = tmem + lane_addr + tmem_s_col + buf * 128 + cgrp * SMX_COLS;
 #pragma unroll
-          for (int c = 0; c < SMX_COLS / 8; ++c) {
-            const uint32_t a = dst + (((cb + c) ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(out[c * 4 + 0]),
-                         "r"(out[c * 4 + 1]), "r"(out[c * 4 + 2]), "r"(out[c * 4 + 3])
-                         : "memory");
+              for (int h = 0; h < SMX_COLS / 32; ++h)
+                tmem_ld_x32(a + 32 * h, *reinterpret_cast<uint32_t(*)[32]>(&v[32 * h]));
+              tmem_ld_wait();
+            }
+            if (pass == SMX_PASSES - 1) {   // S tile fully read: hand the buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
+            }
+
+            const int col0 = t * 128 + cgrp * SMX_COLS;
+            const float4* ymax4 = reinterpret_cast<const float4*>(p.ymax + col0);
+            const float4* ylg4 = reinterpret_cast<const float4*>(p.ylg + col0);
+            uint32_t out[SMX_COLS / 2];
+            const int diag_j = dcol - col0;
+            const bool has_diag = diag_j >= 0 && diag_j < SMX_COLS;
+            const bool any_diag = __any_sync(0xffffffffu, has_diag);
+            float diag_val = 0.f;
+            if (has_diag) diag_val = -(p.w_row * p.xq[row] + p.w_col * p.yq[dcol]);
+            if (kNoSoftmaxMath) {
+#pragma unroll
+              for (int j = 0; j < SMX_COLS / 2; ++j) out[j] = v[2 * j] ^ v[2 * j + 1];
+            } else if (fast) {
+              const float4* yc4 = reinterpret_cast<const float4*>(p.yc + col0);
+              float acc = 0.f;   // carries the 2^13 tile scale
+              if (any_diag)
+                softmax_tile_fast<true>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, diag_val * G_SCALE,
+                                        diag_j, out, acc);
+              else
+                softmax_tile_fast<false>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, 0.f, diag_j, out,
+                                         acc);
+              ds_acc = fmaf(acc, 1.0f / G_SCALE, ds_acc);
+            } else if (any_diag) {
+              softmax_tile<true>(v, ymax4, ylg4, xmax, xlg, scale_log2, diag_val, diag_j, out,
+                                 ds_acc);
+            } else {
+              softmax_tile<false>(v, ymax4, ylg4, xmax, xlg, scale_log2, 0.f, diag_j, out, ds_acc);
+            }
+
+            // stage the fp16 G tile (K-major, 128B swizzle) and push it to the consumer CTA
+            if (!kDecouple && pass == 0 && tile_ctr >= 2)
+              VLP_WAIT(6, mbar_wait_cluster(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
+            // (the tile is two [128 rows x 64 logits] K-major blocks of 16 KB; 16-byte chunks of a
+            // row are XOR-swizzled with the row index)
+            const uint32_t dst = gslots + slot * G_SLOT_BYTES + ((cgrp * SMX_COLS) >> 6) * 16384 +
+                                 row_in_blk * 128;
+            const uint32_t cb = ((cgrp * SMX_COLS) & 63) >> 3;
+#pragma unroll
+            for (int c = 0; c < SMX_COLS / 8; ++c) {
+              const uint32_t a = dst + (((cb + c) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(out[c * 4 + 0]),
+                           "r"(out[c * 4 + 1]), "r"(out[c * 4 + 2]), "r"(out[c * 4 + 3])
+                           : "memory");
+            }
           }
           fence_proxy_async_smem();
-          VLP_WAIT(7, bar_sync(1, 32 * SMX_WARPS));
-          if (warp == 2 && lane == 0) {
+          // the warps that share the tile meet (all softmax warps, or this group in ping-pong mode)
+          VLP_WAIT(7, bar_sync(kPingPong ? 1 + grp : 1, 32 * SMX_TILE_WARPS));
+          const bool pusher = kPingPong ? (((warp - 2) & 3) == 0 && lane == 0) : (warp == 2 && lane == 0);
+          if (!kDecouple && pusher) {
             const uint32_t rbar = mapa_shared(smem_u32(&bars->g_full[slot]), 1);
             const uint32_t rdst = mapa_shared(gslots + slot * G_SLOT_BYTES, 1);
             asm volatile(
@@ -505,8 +563,11 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
       if (p.ds_part != nullptr && lane == 0)
         p.ds_part[(size_t)cluster_id * SMX_WARPS + (warp - 2)] = (float)ds_total;
       // drain: the consumer must have released every slot we pushed before we may exit
-      for (uint32_t back = 0; back < 2 && back < tile_ctr; ++back) {
+      // (ping-pong: a group only ever waited on its own slot, so it drains that one -- the other
+      // slot may still be two phases behind, which a parity wait cannot tell apart)
+      for (uint32_t back = 0; !kDecouple && back < 2 && back < tile_ctr; ++back) {
         const uint32_t tc = tile_ctr - 1 - back;
+        if (kPingPong && (tc & 1) != grp) continue;
         mbar_wait_cluster(smem_u32(&bars->g_empty[tc & 1]), (tc >> 1) & 1);
       }
     }
@@ -524,15 +585,16 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         for (int t = t0; t < t1; ++t)
           for (int nc = 0; nc < n_nc; ++nc) {
             const int nb = min(4, p.ndb - nc * 4);
-            for (int kh = 0; kh < 2; ++kh, ++it) {
+            for (int kh = 0; kh < C_SPLIT; ++kh, ++it) {
               const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
               VLP_WAIT(8, mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1));
+              const int nld = (nb + kConsBoxDiv - 1) / kConsBoxDiv;   // = nb outside the timing mocks
               if (elect_one()) {
-                mbar_expect_tx(smem_u32(&bars->full[st]), nb * 8192);
-                for (int b = 0; b < nb; ++b)
-                  tma_load_2d(ring + st * C_STAGE_BYTES + b * 8192, &map_y_mn,
+                mbar_expect_tx(smem_u32(&bars->full[st]), nld * C_BOX_BYTES);
+                for (int b = 0; b < nld; ++b)
+                  tma_load_2d(ring + st * C_STAGE_BYTES + b * C_BOX_BYTES, &map_y_mn,
                               smem_u32(&bars->full[st]), (p.db0 + nc * 4 + b) * 64,
-                              t * 128 + kh * 64);
+                              t * 128 + kh * C_Q_PER_STAGE);
               }
               __syncwarp();
             }
@@ -550,22 +612,25 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         }
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
           const uint32_t slot = tile_ctr & 1;
-          VLP_WAIT(10, mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
+          if (!kDecouple) VLP_WAIT(10, mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
           tc_fence_after();
           const uint32_t ga = gslots + slot * G_SLOT_BYTES;
           for (int nc = 0; nc < n_nc; ++nc) {
             const int nb = min(4, p.ndb - nc * 4);
             const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
-            for (int kh = 0; kh < 2; ++kh, ++it) {
+            for (int kh = 0; kh < C_SPLIT; ++kh, ++it) {
               const uint32_t st = it % C_STAGES, ph = (it / C_STAGES) & 1;
               VLP_WAIT(11, mbar_wait(smem_u32(&bars->full[st]), ph));
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t sb = ring + st * C_STAGE_BYTES;
+                // G tile = two K-major blocks of [128 rows x 64 q]; stage kh covers q [kh * C_Q, +C_Q)
+                const int q0 = kh * C_Q_PER_STAGE;
+                const uint32_t g0 = ga + (q0 >> 6) * 16384 + ((q0 & 63) >> 4) * 32;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint64_t ad = make_sdesc_sw128(ga + kh * 16384 + i * 32, 0, 1024);
-                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, 8192, 1024);
+                for (int i = 0; i < C_Q_PER_STAGE / 16; ++i) {
+                  const uint64_t ad = make_sdesc_sw128(g0 + i * 32, 0, 1024);
+                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, C_BOX_BYTES, 1024);
                   umma_ss<1>(tmem + nc * 256, ad, bd, idesc, !(t == t0 && kh == 0 && i == 0));
                 }
                 umma_commit<1>(smem_u32(&bars->empty[st]));
@@ -574,7 +639,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
             }
           }
           // release the G slot in the producer CTA (rank 0)
-          if (elect_one()) umma_commit_mcast<1>(smem_u32(&bars->g_empty[slot]), 0x1);
+          if (!kDecouple && elect_one()) umma_commit_mcast<1>(smem_u32(&bars->g_empty[slot]), 0x1);
           __syncwarp();
         }
         if (elect_one()) umma_commit<1>(smem_u32(&bars->acc_full));
@@ -834,11 +899,6 @@ static KernelTimer& kernel_timer() {
   return t;
 }
 
-static long long*& wait_prof_buffer() {
-  static long long* p = nullptr;
-  return p;
-}
-
 static int plan_clusters(int n_row_blocks, int total_tiles) {
   const long long total = (long long)n_row_blocks * total_tiles;
   const int n_pairs = n_pairs_of_device();
@@ -896,6 +956,8 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   p.n_cols = n_cols;
   p.d = d;
   p.kblocks = (d + 63) / 64;
+  if (kPingPong && p.kblocks > 8)
+    return fail(-1, "grad: the ping-pong experiment build needs two S buffers (d <= 512)");
   p.total_tiles = (n_cols + 127) / 128;
   p.n_row_blocks = (n_rows + 127) / 128;
   const int clusters = plan_clusters(p.n_row_blocks, p.total_tiles);
@@ -960,7 +1022,7 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   CUtensorMap map_k, map_mn;
   rc = make_tmap_sw128(&map_k, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
   if (rc) return rc;
-  rc = make_tmap_sw128(&map_mn, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 64);
+  rc = make_tmap_sw128(&map_mn, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, C_Q_PER_STAGE);
   if (rc) return rc;
 
   static_assert(sizeof(BwdBarriers) <= BAR_BYTES, "barrier block");

@@ -16,19 +16,35 @@
 // Work item = (row block, chunk of column tiles); partial (m, l) pairs per (chunk, half) go to
 // a workspace and are merged by lse_merge_kernel in fixed order (bit reproducible).
 #include <cuda_bf16.h>
-#include "common.cuh"
-#include "../../include/vlpclip.h"
+#include "pipeline_exp.cuh"
+#include "../../../include/vlpclip.h"
 
 namespace vlp {
 
-constexpr int FWD_KB_PER_STAGE = 2;          // k-blocks (128 rows x 64 bf16 = 16 KB boxes) per stage
+#ifndef VLP_FWD_KB_PER_STAGE
+#define VLP_FWD_KB_PER_STAGE 2               // (overridable for tools/pipeline_experiments.py)
+#endif
+constexpr int FWD_KB_PER_STAGE = VLP_FWD_KB_PER_STAGE;   // k-blocks (128 rows x 64 bf16 = 16 KB boxes) per stage
 constexpr int FWD_BOX_BYTES = 128 * 128;
 constexpr int FWD_STAGE_BYTES = FWD_KB_PER_STAGE * FWD_BOX_BYTES;
-constexpr int FWD_STAGES = 6;
+constexpr int FWD_STAGES = 6 * 2 / FWD_KB_PER_STAGE;     // 192 KB ring: 6 stages of 32 KB
 constexpr int FWD_SMW = 16;                  // softmax warps: 4 TMEM lane quarters x 4 column groups
 constexpr int FWD_CG = FWD_SMW / 4;          // column groups per tile
 constexpr int FWD_CPT = 128 / FWD_CG;        // columns per thread (32)
 constexpr int FWD_THREADS = 64 + FWD_SMW * 32;
+// experiment switches of tools/pipeline_experiments.py (never set in the shipped library):
+// VLP_EXP_HALF_Y_F  timing mock, the TMA warp fetches half of the boxes of each ring stage
+// VLP_EXP_NO_SMX_F  timing mock, softmax warps only drain the S buffer
+#ifdef VLP_EXP_HALF_Y_F
+constexpr int kFwdBoxDiv = 2;
+#else
+constexpr int kFwdBoxDiv = 1;
+#endif
+#ifdef VLP_EXP_NO_SMX_F
+constexpr bool kFwdNoSoftmax = true;
+#else
+constexpr bool kFwdNoSoftmax = false;
+#endif
 constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: d/2 columns (256 at d = 512, 384 at d = 768)
 // S buffers of 128 columns sit at the top of TMEM: two (double buffered) while d <= 512, a single
 // one for 512 < d <= 768 (MMA and softmax of consecutive tiles then serialise)
@@ -52,6 +68,7 @@ struct LseParams {
   // sum_i exp2(k c_ij - ref) with a log2-domain reference `ref`; the positive pair is left out
   float* col_ref;       // [n_row_blocks][total_tiles * 128]
   float* col_l;         // [n_row_blocks][total_tiles * 128]
+  long long* wait_prof; // [n_sm][8] blocked-cycle counters (VLP_PROFILE_WAITS builds only)
 };
 
 struct FwdBarriers {
@@ -70,9 +87,17 @@ struct FwdBarriers {
 constexpr float COL_HEADROOM = 100.f;  // partial sums carry 2^100: 226 log2 units of range below a
                                        // warp's largest row maximum before a term can underflow
 
-template <bool kCols>
+// CG = 1: one CTA per row block (shipped path).  CG = 2 (experiment build -DVLP_FWD_PAIR): a
+// cluster of two CTAs sweeps two adjacent row blocks over the same column tiles with cta_group::2
+// MMAs (M = 256): each CTA stages only ITS half of every Y tile (64 of the 128 columns), the leader
+// CTA issues the MMAs for both, every CTA finds the S rows of its own row block in its own TMEM.
+// Barriers the MMA warp waits on (x_ready, s_empty, full) live in the leader and collect the
+// arrivals of both CTAs; barriers it signals (empty, s_full, x_free) are multicast to both.
+template <bool kCols, int CG>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p) {
+  constexpr int KBS = FWD_KB_PER_STAGE * CG;        // k-blocks per ring stage
+  constexpr int BOX = FWD_BOX_BYTES / CG;           // [128 / CG columns x 64 k] box
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -80,6 +105,12 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
   const uint32_t ring = smem_u32(smem);
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+#ifdef VLP_PROFILE_WAITS
+  long long wait_cyc[8] = {0};
+  const long long kernel_t0 = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < FWD_STAGES; ++i) {
@@ -88,20 +119,24 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->s_empty[i]), FWD_SMW);  // one arrive per softmax warp
+      mbar_init(smem_u32(&bars->s_empty[i]), FWD_SMW * CG);  // one arrive per softmax warp
     }
-    mbar_init(smem_u32(&bars->x_ready), FWD_SMW);
+    mbar_init(smem_u32(&bars->x_ready), FWD_SMW * CG);
     mbar_init(smem_u32(&bars->x_free), 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<1>(smem_u32(&bars->tmem_base), 512);
+  if (warp == 1) tmem_alloc<CG>(smem_u32(&bars->tmem_base), 512);
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_y);
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  const int n_items = p.n_row_blocks * p.n_chunks;
+  // work items: (unit of CG adjacent row blocks, column chunk), one cluster (CTA) per item
+  const int n_rbu = (p.n_row_blocks + CG - 1) / CG;
+  const int n_items = n_rbu * p.n_chunks;
+  const int unit0 = blockIdx.x / CG, n_units = gridDim.x / CG;
   const float scale_log2 = __ldg(p.scale_ptr) * kLog2e;   // k = s * log2(e), device-side scalar
   const uint32_t nbuf = p.kblocks <= 8 ? 2u : 1u;
   const uint32_t tmem_s_col = 512u - nbuf * 128u;
@@ -109,70 +144,104 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
   if (warp == 0) {
     // ================= TMA producer (whole warp converged, one elected lane issues) ==========
     uint32_t it = 0;  // running stage counter
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item / p.n_row_blocks;
+    for (int item = unit0; item < n_items; item += n_units) {
+      const int chunk = item / n_rbu;
       const int t0 = chunk * p.tiles_per_chunk;
       const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
       for (int t = t0; t < t1; ++t) {
-        for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE, ++it) {
+        for (int kb = 0; kb < p.kblocks; kb += KBS, ++it) {
           const uint32_t st = it % FWD_STAGES;
           const uint32_t ph = (it / FWD_STAGES) & 1;
-          const int nkb = min(FWD_KB_PER_STAGE, p.kblocks - kb);
-          mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+          const int nkb = min(KBS, p.kblocks - kb);
+          const int nld = (nkb + kFwdBoxDiv - 1) / kFwdBoxDiv;   // = nkb outside the timing mock
+          if (CG == 2)
+            VLP_WAIT(0, mbar_wait_cluster(smem_u32(&bars->empty[st]), ph ^ 1));
+          else
+            VLP_WAIT(0, mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1));
           if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bars->full[st]), nkb * FWD_BOX_BYTES);
-            for (int q = 0; q < nkb; ++q)
-              tma_load_2d(ring + st * FWD_STAGE_BYTES + q * FWD_BOX_BYTES, &map_y,
-                          smem_u32(&bars->full[st]), (kb + q) * 64, t * 128);
+            // pair: the leader's barrier counts the bytes of both CTAs
+            if (leader) mbar_expect_tx(smem_u32(&bars->full[st]), nld * BOX * CG);
+            for (int q = 0; q < nld; ++q) {
+              if (CG == 2)
+                tma_load_2d_pair(ring + st * FWD_STAGE_BYTES + q * BOX, &map_y,
+                                 smem_u32(&bars->full[st]), (kb + q) * 64, t * 128 + rank * 64);
+              else
+                tma_load_2d(ring + st * FWD_STAGE_BYTES + q * BOX, &map_y,
+                            smem_u32(&bars->full[st]), (kb + q) * 64, t * 128);
+            }
           }
           __syncwarp();
         }
+      }
+    }
+    if (CG == 2) {
+      // tail: the multicast commits that release the last ring stages must have landed in THIS
+      // CTA before it may exit (the warp has waited on every earlier phase, so parities are adjacent)
+      const uint32_t last = it < (uint32_t)FWD_STAGES ? it : (uint32_t)FWD_STAGES;
+      for (uint32_t k = 0; k < last; ++k) {
+        const uint32_t j = it - 1 - k;
+        mbar_wait_cluster(smem_u32(&bars->empty[j % FWD_STAGES]), (j / FWD_STAGES) & 1);
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp converged, one elected lane issues) ===========
     const uint32_t fmt = p.operand_f16 ? UMMA_F16 : UMMA_BF16;
-    const uint32_t idesc = make_idesc(fmt, fmt, MAJOR_K, MAJOR_K, 128, 128);
+    const uint32_t idesc = make_idesc(fmt, fmt, MAJOR_K, MAJOR_K, 128 * CG, 128);
+    // signal a barrier when the MMAs issued so far complete (pair: same barrier in both CTAs)
+    auto commit = [&](uint64_t* bar) {
+      if (CG == 2)
+        umma_commit_mcast<CG>(smem_u32(bar), 0x3);
+      else
+        umma_commit<CG>(smem_u32(bar));
+    };
     uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
-      const int chunk = item / p.n_row_blocks;
+    for (int item = unit0; item < n_items; item += n_units, ++item_ctr) {
+      if (!leader) continue;   // the peer's MMA warp idles (it only takes part in the TMEM alloc)
+      const int chunk = item / n_rbu;
       const int t0 = chunk * p.tiles_per_chunk;
       const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-      mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
+      if (CG == 2)
+        VLP_WAIT(1, mbar_wait_cluster(smem_u32(&bars->x_ready), item_ctr & 1));
+      else
+        VLP_WAIT(1, mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1));
       tc_fence_after();
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
         const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-        mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1);
+        if (CG == 2)
+          VLP_WAIT(2, mbar_wait_cluster(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1));
+        else
+          VLP_WAIT(2, mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1));
         tc_fence_after();
         const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
-        for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE, ++it) {
+        for (int kb = 0; kb < p.kblocks; kb += KBS, ++it) {
           const uint32_t st = it % FWD_STAGES;
           const uint32_t ph = (it / FWD_STAGES) & 1;
-          const int nkb = min(FWD_KB_PER_STAGE, p.kblocks - kb);
-          mbar_wait(smem_u32(&bars->full[st]), ph);
+          const int nkb = min(KBS, p.kblocks - kb);
+          VLP_WAIT(3, mbar_wait(smem_u32(&bars->full[st]), ph));
           tc_fence_after();
           if (elect_one()) {
             for (int q = 0; q < nkb; ++q) {
-              const uint32_t sb = ring + st * FWD_STAGE_BYTES + q * FWD_BOX_BYTES;
+              const uint32_t sb = ring + st * FWD_STAGE_BYTES + q * BOX;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                umma_ts<1>(d_tmem, tmem + TMEM_X_COL + (kb + q) * 32 + ks * 8,
-                           make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | q | ks) != 0);
+                umma_ts<CG>(d_tmem, tmem + TMEM_X_COL + (kb + q) * 32 + ks * 8,
+                            make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | q | ks) != 0);
               }
             }
-            umma_commit<1>(smem_u32(&bars->empty[st]));
+            commit(&bars->empty[st]);
           }
           __syncwarp();
         }
-        if (elect_one()) umma_commit<1>(smem_u32(&bars->s_full[buf]));
+        if (elect_one()) commit(&bars->s_full[buf]);
         __syncwarp();
       }
-      if (elect_one()) umma_commit<1>(smem_u32(&bars->x_free));
+      if (elect_one()) commit(&bars->x_free);
       __syncwarp();
     }
-    // do not exit with an arrive still in flight
-    if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+    // do not exit with an arrive still in flight (pair: the tails of the TMA and softmax warps of
+    // both CTAs wait for the multicast commits instead)
+    if (CG == 1 && item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
   } else {
     // ================= softmax warps =================
     // thread = (row, column group): quarter = TMEM lane quarter of the warp, cg = 32-column group
@@ -183,9 +252,16 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     const uint32_t lane_addr = (quarter * 32u) << 16;
     const int dp = p.kblocks * 64;               // padded K
     uint32_t tile_ctr = 0, item_ctr = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
-      const int chunk = item / p.n_row_blocks;
-      const int rb = item % p.n_row_blocks;
+    // arrive on a barrier the MMA warp waits on: it lives in the leader CTA
+    auto arrive_leader = [&](uint64_t* bar) {
+      if (CG == 1 || leader)
+        mbar_arrive(smem_u32(bar));
+      else
+        mbar_arrive_cluster(mapa_shared(smem_u32(bar), 0));
+    };
+    for (int item = unit0; item < n_items; item += n_units, ++item_ctr) {
+      const int chunk = item / n_rbu;
+      const int rb = (item % n_rbu) * CG + (int)rank;   // pair: may be one past the last row block
       const int t0 = chunk * p.tiles_per_chunk;
       const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
       const int row = rb * 128 + row_in_blk;
@@ -193,7 +269,10 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
 
       // ---- stage the X row block into TMEM (bf16 pairs packed per 32-bit column) ----
       if (item_ctr > 0) {
-        mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+        if (CG == 2)
+          VLP_WAIT(4, mbar_wait_cluster(smem_u32(&bars->x_free), (item_ctr - 1) & 1));
+        else
+          VLP_WAIT(4, mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1));
         tc_fence_after();
       }
       {
@@ -216,7 +295,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
+        if (lane == 0) arrive_leader(&bars->x_ready);
       }
 
       float m_run = -INFINITY, mraw_run = -INFINITY, l_run = 0.f;
@@ -225,14 +304,21 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
         const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-        mbar_wait(smem_u32(&bars->s_full[buf]), use & 1);
+        if (CG == 2)
+          VLP_WAIT(5, mbar_wait_cluster(smem_u32(&bars->s_full[buf]), use & 1));
+        else
+          VLP_WAIT(5, mbar_wait(smem_u32(&bars->s_full[buf]), use & 1));
         tc_fence_after();
         uint32_t v[FWD_CPT];
         tmem_ld_x32(tmem + lane_addr + tmem_s_col + buf * 128 + cg * FWD_CPT, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
+        if (lane == 0) arrive_leader(&bars->s_empty[buf]);
+        if (kFwdNoSoftmax) {   // timing mock: keep the loads observable, skip the arithmetic
+          mraw_run = fmaxf(mraw_run, __uint_as_float(v[lane & (FWD_CPT - 1)]));
+          continue;
+        }
 
         const int col0 = t * 128 + cg * FWD_CPT;
         // columns past n_cols were zero-filled by TMA: mask them out of the statistics
@@ -303,9 +389,9 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           const uint32_t par = tile_ctr & 1;
           bars->col_s[par][wslot][lane] = c[0];
           if (lane == 0) bars->col_r[par][wslot] = R - COL_HEADROOM;
-          bar_sync(2, FWD_SMW * 32);
+          VLP_WAIT(6, bar_sync(2, FWD_SMW * 32));
           const uint32_t st = wslot * 32 + lane;   // the first 128 softmax threads own one column
-          if (st < 128) {
+          if (st < 128 && (CG == 1 || rb < p.n_row_blocks)) {   // pair: skip a phantom row block
             const uint32_t g = st >> 5, cc = st & 31;   // warps of column group g: slots g*4 .. g*4+3
             float r4[4], l4[4], M = -INFINITY;
 #pragma unroll
@@ -330,11 +416,22 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         p.part_l[o] = l_run;
       }
     }
+    // pair: the multicast commit that frees the last X block must have landed before the CTA exits
+    if (CG == 2 && item_ctr > 0) mbar_wait_cluster(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
   }
 
+#ifdef VLP_PROFILE_WAITS
+  if (p.wait_prof != nullptr && lane == 0 && warp <= 2) {
+    long long* o = p.wait_prof + (size_t)blockIdx.x * 8;   // indices are disjoint between roles
+    for (int i = 0; i < 7; ++i)
+      if (wait_cyc[i] != 0) o[i] = wait_cyc[i];
+    if (warp == 0) o[7] = clock64() - kernel_t0;
+  }
+#endif
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<1>(tmem, 512);
+  if (CG == 2) cluster_sync_all();
+  if (warp == 1) tmem_dealloc<CG>(tmem, 512);
 }
 
 // Merge [nparts][n] partial (max, l) pairs in fixed order.
@@ -608,9 +705,17 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   p.total_tiles = (n_cols + 127) / 128;
   p.n_row_blocks = (n_rows + 127) / 128;
   const int nsm = usable_sms();
-  pick_chunks(p.n_row_blocks, p.total_tiles, nsm, &p.n_chunks, &p.tiles_per_chunk);
+#ifdef VLP_FWD_PAIR
+  constexpr int kFwdCG = 2;   // experiment build: cta_group::2 forward (tools/pipeline_experiments.py)
+#else
+  constexpr int kFwdCG = 1;
+#endif
+  const int n_units_max = nsm / kFwdCG;                               // CTAs, or CTA pairs
+  const int n_rbu = (p.n_row_blocks + kFwdCG - 1) / kFwdCG;           // row blocks (or pairs of them)
+  pick_chunks(n_rbu, p.total_tiles, n_units_max, &p.n_chunks, &p.tiles_per_chunk);
   p.diag_shift = diag_shift;
   p.scale_ptr = scale;
+  p.wait_prof = wait_prof_buffer() ? wait_prof_buffer() + WAIT_PROF_BWD_WORDS : nullptr;
   const int nparts = p.n_chunks * FWD_CG;
   p.part_m = (float*)workspace;
   p.part_l = p.part_m + (size_t)nparts * n_rows;
@@ -624,24 +729,36 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   }
 
   CUtensorMap map_y;
-  rc = make_tmap_sw128(&map_y, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
+  rc = make_tmap_sw128(&map_y, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128 / kFwdCG);
   if (rc) return rc;
 
   const size_t smem = FWD_STAGES * FWD_STAGE_BYTES + sizeof(FwdBarriers) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel<false>,
+    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel<false, kFwdCG>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel<true>,
+    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel<true, kFwdCG>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int n_items = p.n_row_blocks * p.n_chunks;
-  const int grid = n_items < nsm ? n_items : nsm;
+  const int n_items = n_rbu * p.n_chunks;
+  const int grid = (n_items < n_units_max ? n_items : n_units_max) * kFwdCG;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(FWD_THREADS);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kFwdCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  lc.attrs = attr;
+  lc.numAttrs = kFwdCG > 1 ? 1 : 0;
   if (fused)
-    lse_partial_kernel<true><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+    VLP_CUDA_OK(cudaLaunchKernelEx(&lc, lse_partial_kernel<true, kFwdCG>, map_y, p));
   else
-    lse_partial_kernel<false><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+    VLP_CUDA_OK(cudaLaunchKernelEx(&lc, lse_partial_kernel<false, kFwdCG>, map_y, p));
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   lse_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_m, p.part_l, nullptr, nparts,
