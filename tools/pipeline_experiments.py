@@ -39,6 +39,10 @@ VARIANTS = {
                    "16 KB ring stages everywhere (8 / 8 / 12 stages): fewer bytes pinned under the MMAs"),
     "fine_rings_pingpong": ("real", ["VLP_P_KB_PER_STAGE=1", "VLP_C_Q_PER_STAGE=32", "VLP_FWD_KB_PER_STAGE=1",
                                      "VLP_BWD_PINGPONG"], "both real variants together"),
+    "push4": ("real", ["VLP_PUSH_SPLIT=4"], "G tile pushed to the consumer as 4 concurrent 8 KB bulk copies"),
+    "g3": ("real", ["VLP_G_SLOTS=3"], "three G slots (consumer ring 3 x 32 KB): looser producer/consumer coupling"),
+    "g3_push4_fine": ("real", ["VLP_G_SLOTS=3", "VLP_PUSH_SPLIT=4", "VLP_P_KB_PER_STAGE=1", "VLP_C_Q_PER_STAGE=32",
+                               "VLP_FWD_KB_PER_STAGE=1"], "three G slots + split push + 16 KB ring stages"),
     "no_smx": ("mock", ["VLP_EXP_NO_SMX", "VLP_EXP_NO_SMX_F"], "softmax arithmetic removed (fwd + bwd)"),
     "bwd_decouple": ("mock", ["VLP_EXP_DECOUPLE"], "no G hand-off: each backward role at its own pace"),
     "bwd_decouple_half_y": ("mock", ["VLP_EXP_DECOUPLE", "VLP_EXP_HALF_Y_P", "VLP_EXP_HALF_Y_C"],

@@ -43,6 +43,9 @@ constexpr int BWD_THREADS = 64 + 32 * SMX_WARPS;   // TMA warp + MMA warp + soft
 //                    half of the boxes of every ring stage (the MMAs read stale bytes): what a
 //                    cta_group::2 kernel would stream per SM.  Results are garbage by construction.
 // VLP_EXP_NO_SMX     timing mock: softmax warps skip the arithmetic (G tile = raw bits of S)
+// VLP_G_SLOTS=3      real variant: three G tiles in flight (consumer ring shrinks to 96 KB)
+// VLP_PUSH_SPLIT=n   real variant: a G tile crosses the pair as n concurrent bulk copies
+// VLP_P_KB_PER_STAGE / VLP_C_Q_PER_STAGE   real variants: ring stage granularity
 // VLP_EXP_DECOUPLE   timing mock: no G hand-off (producer does not push, consumer does not wait):
 //                    each role runs at its own pace; read the per-role cycles of the wait profile
 #ifdef VLP_BWD_PINGPONG
@@ -70,7 +73,6 @@ constexpr bool kDecouple = true;
 #else
 constexpr bool kDecouple = false;
 #endif
-static_assert(!kPingPong || SMX_GROUPS == 2, "ping-pong: one warp group per S buffer / G slot");
 constexpr int SMX_PASSES = kPingPong ? 2 : 1;                 // SMX_COLS-wide passes per thread and tile
 constexpr int SMX_TILE_WARPS = kPingPong ? 4 : SMX_WARPS;     // warps that share one S tile
 // ring geometry (overridable for tools/pipeline_experiments.py: finer stages pin fewer bytes under
@@ -81,21 +83,35 @@ constexpr int SMX_TILE_WARPS = kPingPong ? 4 : SMX_WARPS;     // warps that shar
 #ifndef VLP_C_Q_PER_STAGE
 #define VLP_C_Q_PER_STAGE 64
 #endif
-constexpr int RING_BYTES = 131072;          // both rings occupy the first 128 KB
+#ifndef VLP_G_SLOTS
+#define VLP_G_SLOTS 2
+#endif
+#ifndef VLP_PUSH_SPLIT
+#define VLP_PUSH_SPLIT 1
+#endif
+constexpr int G_SLOTS = VLP_G_SLOTS;        // G tiles in flight between producer and consumer
+constexpr int PUSH_SPLIT = VLP_PUSH_SPLIT;  // concurrent bulk copies one G tile is pushed with
+static_assert(G_SLOTS == 2 || G_SLOTS == 3, "G slots");
+static_assert(PUSH_SPLIT == 1 || PUSH_SPLIT == 2 || PUSH_SPLIT == 4 || PUSH_SPLIT == 8, "push split");
+static_assert(!kPingPong || (SMX_GROUPS == 2 && G_SLOTS == 2), "ping-pong: one warp group per S buffer / G slot");
+// shared memory: [G slots][barriers][ring][consumer epilogue tile]; the G slots and barriers sit
+// at the same offsets in both CTAs (they are addressed across the pair), the ring is per role:
+// 128 KB for the producer, 128 KB (96 KB with three G slots) for the consumer
+constexpr int P_RING_BYTES = 131072;
+constexpr int C_RING_BYTES = G_SLOTS == 3 ? 98304 : 131072;
 constexpr int P_KB_PER_STAGE = VLP_P_KB_PER_STAGE;   // producer ring stage: boxes of [128 q x 64 k] fp16
 constexpr int P_BOX_BYTES = 16384;
 constexpr int P_STAGE_BYTES = P_KB_PER_STAGE * P_BOX_BYTES;
-constexpr int P_STAGES = RING_BYTES / P_STAGE_BYTES;                // 4 stages of 32 KB
+constexpr int P_STAGES = P_RING_BYTES / P_STAGE_BYTES;              // 4 stages of 32 KB
 constexpr int C_Q_PER_STAGE = VLP_C_Q_PER_STAGE;     // consumer ring stage: [64 q x 256 d] fp16 = 32 KB
 constexpr int C_BOX_BYTES = C_Q_PER_STAGE * 128;     // one [q x 64 d] box
 constexpr int C_STAGE_BYTES = 4 * C_BOX_BYTES;
-constexpr int C_STAGES = RING_BYTES / C_STAGE_BYTES;                // 4 stages of 32 KB
+constexpr int C_STAGES = C_RING_BYTES / C_STAGE_BYTES;              // 4 stages of 32 KB
 constexpr int C_SPLIT = 128 / C_Q_PER_STAGE;         // stages per (tile, 256-column accumulator chunk)
 constexpr int RING_BARS = P_STAGES > C_STAGES ? P_STAGES : C_STAGES;
 static_assert(P_KB_PER_STAGE == 1 || P_KB_PER_STAGE == 2 || P_KB_PER_STAGE == 4, "producer stage");
 static_assert(C_Q_PER_STAGE == 32 || C_Q_PER_STAGE == 64, "consumer stage");
 constexpr int G_SLOT_BYTES = 32768;         // [128 rows x 128 q] fp16
-constexpr int G_SLOTS = 2;
 constexpr int BAR_BYTES = 1024;               // barrier block
 constexpr int EPI_STAGE_BYTES = 4 * 4096;    // consumer epilogue: one 32 x 32 fp32 tile per warp
 constexpr uint32_t BWD_TMEM_X = 0;          // producer: X block (fp16 packed), d/2 columns
@@ -305,11 +321,10 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  BwdBarriers* bars =
-      reinterpret_cast<BwdBarriers*>(smem + RING_BYTES + G_SLOTS * G_SLOT_BYTES);
-  const uint32_t ring = smem_u32(smem);
-  const uint32_t gslots = ring + RING_BYTES;
-  const uint32_t stage = gslots + G_SLOTS * G_SLOT_BYTES + BAR_BYTES;
+  BwdBarriers* bars = reinterpret_cast<BwdBarriers*>(smem + G_SLOTS * G_SLOT_BYTES);
+  const uint32_t gslots = smem_u32(smem);
+  const uint32_t ring = gslots + G_SLOTS * G_SLOT_BYTES + BAR_BYTES;
+  const uint32_t stage = ring + C_RING_BYTES;   // consumer only
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -328,6 +343,8 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
       mbar_init(smem_u32(&bars->s_empty[i]), SMX_TILE_WARPS);
+    }
+    for (int i = 0; i < G_SLOTS; ++i) {
       mbar_init(smem_u32(&bars->g_full[i]), 1);
       mbar_init(smem_u32(&bars->g_empty[i]), 1);
     }
@@ -474,7 +491,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
           VLP_WAIT(5, mbar_wait(smem_u32(&bars->s_full[buf]), use & 1));
           tc_fence_after();
-          const uint32_t slot = tile_ctr & 1;
+          const uint32_t slot = tile_ctr % G_SLOTS, slot_use = tile_ctr / G_SLOTS;
 #pragma unroll 1
           for (int pass = 0; pass < SMX_PASSES; ++pass) {
             const uint32_t cgrp = kPingPong ? (uint32_t)pass : grp;   // SMX_COLS-wide column group
@@ -522,8 +539,8 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
             }
 
             // stage the fp16 G tile (K-major, 128B swizzle) and push it to the consumer CTA
-            if (!kDecouple && pass == 0 && tile_ctr >= 2)
-              VLP_WAIT(6, mbar_wait_cluster(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
+            if (!kDecouple && pass == 0 && slot_use > 0)
+              VLP_WAIT(6, mbar_wait_cluster(smem_u32(&bars->g_empty[slot]), (slot_use - 1) & 1));
             // (the tile is two [128 rows x 64 logits] K-major blocks of 16 KB; 16-byte chunks of a
             // row are XOR-swizzled with the row index)
             const uint32_t dst = gslots + slot * G_SLOT_BYTES + ((cgrp * SMX_COLS) >> 6) * 16384 +
@@ -540,19 +557,24 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           fence_proxy_async_smem();
           // the warps that share the tile meet (all softmax warps, or this group in ping-pong mode)
           VLP_WAIT(7, bar_sync(kPingPong ? 1 + grp : 1, 32 * SMX_TILE_WARPS));
-          const bool pusher = kPingPong ? (((warp - 2) & 3) == 0 && lane == 0) : (warp == 2 && lane == 0);
-          if (!kDecouple && pusher) {
+          // one warp pushes the tile: lane 0 arms the consumer's barrier with the whole byte count,
+          // lanes 0 .. PUSH_SPLIT-1 each copy one chunk (concurrent bulk copies)
+          const bool push_warp = kPingPong ? (((warp - 2) & 3) == 0) : (warp == 2);
+          if (!kDecouple && push_warp && lane < (uint32_t)PUSH_SPLIT) {
+            constexpr uint32_t kChunk = G_SLOT_BYTES / PUSH_SPLIT;
             const uint32_t rbar = mapa_shared(smem_u32(&bars->g_full[slot]), 1);
-            const uint32_t rdst = mapa_shared(gslots + slot * G_SLOT_BYTES, 1);
-            asm volatile(
-                "mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
-                    rbar),
-                "r"(G_SLOT_BYTES)
-                : "memory");
+            const uint32_t src = gslots + slot * G_SLOT_BYTES + lane * kChunk;
+            const uint32_t rdst = mapa_shared(src, 1);
+            if (lane == 0)
+              asm volatile(
+                  "mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
+                      rbar),
+                  "r"(G_SLOT_BYTES)
+                  : "memory");
             asm volatile(
                 "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], "
                 "%2, [%3];" ::"r"(rdst),
-                "r"(gslots + slot * G_SLOT_BYTES), "r"(G_SLOT_BYTES), "r"(rbar)
+                "r"(src), "r"(kChunk), "r"(rbar)
                 : "memory");
           }
         }
@@ -565,10 +587,10 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
       // drain: the consumer must have released every slot we pushed before we may exit
       // (ping-pong: a group only ever waited on its own slot, so it drains that one -- the other
       // slot may still be two phases behind, which a parity wait cannot tell apart)
-      for (uint32_t back = 0; !kDecouple && back < 2 && back < tile_ctr; ++back) {
+      for (uint32_t back = 0; !kDecouple && back < (uint32_t)G_SLOTS && back < tile_ctr; ++back) {
         const uint32_t tc = tile_ctr - 1 - back;
         if (kPingPong && (tc & 1) != grp) continue;
-        mbar_wait_cluster(smem_u32(&bars->g_empty[tc & 1]), (tc >> 1) & 1);
+        mbar_wait_cluster(smem_u32(&bars->g_empty[tc % G_SLOTS]), (tc / G_SLOTS) & 1);
       }
     }
   } else {
@@ -611,8 +633,9 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
           tc_fence_after();
         }
         for (int t = t0; t < t1; ++t, ++tile_ctr) {
-          const uint32_t slot = tile_ctr & 1;
-          if (!kDecouple) VLP_WAIT(10, mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
+          const uint32_t slot = tile_ctr % G_SLOTS;
+          if (!kDecouple)
+            VLP_WAIT(10, mbar_wait_cluster(smem_u32(&bars->g_full[slot]), (tile_ctr / G_SLOTS) & 1));
           tc_fence_after();
           const uint32_t ga = gslots + slot * G_SLOT_BYTES;
           for (int nc = 0; nc < n_nc; ++nc) {
@@ -1026,7 +1049,10 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   if (rc) return rc;
 
   static_assert(sizeof(BwdBarriers) <= BAR_BYTES, "barrier block");
-  const size_t smem = RING_BYTES + G_SLOTS * G_SLOT_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;
+  constexpr size_t kRoleBytes = (size_t)P_RING_BYTES > (size_t)C_RING_BYTES + EPI_STAGE_BYTES
+                                    ? (size_t)P_RING_BYTES : (size_t)C_RING_BYTES + EPI_STAGE_BYTES;
+  const size_t smem = G_SLOTS * G_SLOT_BYTES + BAR_BYTES + kRoleBytes + 1024;
+  static_assert(G_SLOTS * G_SLOT_BYTES + BAR_BYTES + kRoleBytes + 1024 <= 232448, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
     VLP_CUDA_OK(cudaFuncSetAttribute(grad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
