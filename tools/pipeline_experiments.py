@@ -9,8 +9,10 @@ pass, plus the blocked-cycle profile of every pipeline role (all variants carry
 -DVLP_PROFILE_WAITS).  Variants marked "real" are also checked against a torch fp32 reference;
 "mock" variants compute garbage by construction and are timing-only.
 
-    python tools/pipeline_experiments.py build                 (CPU box: cross-compile all variants)
-    python tools/pipeline_experiments.py run [N] [D]           (B200; writes gpurun_out/pipeline_experiments.txt)
+    python tools/pipeline_experiments.py build                 (cross-compile all variants; compile check)
+    python tools/pipeline_experiments.py run [N] [D]           (B200; builds what is missing -- tools/variants/
+                                                                does not travel with gpurun -- and writes
+                                                                gpurun_out/pipeline_experiments.txt)
     python tools/pipeline_experiments.py one <name> [N] [D]    (B200; one variant, this process)
 """
 import math
@@ -67,13 +69,22 @@ def next_sources():
             os.path.join(_build.CSRC, "prologue.cu")]
 
 
-def build():
+def build(only_missing=False):
+    """Cross-compile every variant (8 nvcc processes at a time)."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(VAR_DIR, exist_ok=True)
-    for name, (_, defs, _) in VARIANTS.items():
+
+    def one_build(name):
+        defs = VARIANTS[name][1]
         cmd = [_build._nvcc()] + _build.NVCC_FLAGS + ["-DVLP_PROFILE_WAITS"] + [f"-D{d}" for d in defs] + \
               ["-o", lib_of(name)] + next_sources()
         subprocess.run(cmd, check=True)
-        print("built", lib_of(name))
+        return name
+
+    todo = [n for n in VARIANTS if not (only_missing and os.path.exists(lib_of(n)))]
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for name in ex.map(one_build, todo):
+            print("built", lib_of(name), flush=True)
 
 
 def _reference(I, T, s):
@@ -187,6 +198,7 @@ def run(n, d):
     out_dir = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
     log = open(os.path.join(out_dir, "pipeline_experiments.txt"), "w")
+    build(only_missing=True)   # tools/variants/ is gpurun-ignored: missing libraries are built on the box
     for name in VARIANTS:
         if not os.path.exists(lib_of(name)):
             line = f"[{name}] library missing: run `python tools/pipeline_experiments.py build` first\n"
