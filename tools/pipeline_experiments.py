@@ -33,6 +33,10 @@ VARIANTS = {
                      "softmax warp groups alternate whole tiles (2 tile times per tile and group)"),
     "fwd_pair": ("real", ["VLP_FWD_PAIR"],
                  "forward on CTA pairs with cta_group::2 MMAs: each SM stages half of every Y tile"),
+    "bwd_quad": ("real", ["VLP_BWD_QUAD"],
+                 "backward on clusters of 4 CTAs with cta_group::2 MMAs: every SM stages half of each Y tile "
+                 "(its cycles/tile are per 4 SMs: equal throughput = HALF the pair kernel's figure)"),
+    "bwd_quad_push4": ("real", ["VLP_BWD_QUAD", "VLP_PUSH_SPLIT=4"], "quad backward + split push"),
     "half_y_fwd": ("mock", ["VLP_EXP_HALF_Y_F"], "forward streams half of Y per SM (cta_group::2 traffic)"),
     "half_y_bwd_p": ("mock", ["VLP_EXP_HALF_Y_P"], "backward producer streams half of Y"),
     "half_y_bwd_c": ("mock", ["VLP_EXP_HALF_Y_C"], "backward consumer streams half of Y"),

@@ -767,6 +767,12 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
 }
 
+}  // namespace vlp
+#ifdef VLP_BWD_QUAD
+#include "grad_bwd_quad.cuh"
+#endif
+namespace vlp {
+
 // Global range of the log2-domain LSEs (rows of X and of Y, direction weights folded in), stage 1:
 // RANGE_BLOCKS blocks each write their (min, max) to part[2 * block].
 constexpr int RANGE_BLOCKS = 32;
@@ -849,13 +855,17 @@ __global__ void stats_pad_kernel(const float* __restrict__ mx, const float* __re
 // Row blocks whose column sweep was split between clusters: dx rows = mul * (sum of the partial
 // blocks in cluster order).  One block row of the grid per row block; unsplit ones return at once.
 constexpr int RED_SPLIT = 32;
-__global__ void dx_reduce_kernel(const float* __restrict__ part, int n_clusters, int n_row_blocks,
+// rpu = row blocks per work unit (1: pair kernel; 2: quad kernel, whose units are row-block pairs and
+// whose partial slots hold one 128 x d block per row block of the unit)
+__global__ void dx_reduce_kernel(const float* __restrict__ part, int n_clusters, int n_units,
                                  int tiles, int n_rows, int d, const float* __restrict__ out_mul,
-                                 int out_bf16, void* __restrict__ dx, const RowScatter scatter) {
+                                 int out_bf16, void* __restrict__ dx, const RowScatter scatter,
+                                 int rpu) {
   const int rb = blockIdx.x;
-  const long long total = (long long)n_row_blocks * tiles;
+  const int unit = rb / rpu, sub = rb - unit * rpu;
+  const long long total = (long long)n_units * tiles;
   SplitBlock sb;
-  if (!split_block(rb, tiles, n_clusters, total, sb)) return;
+  if (!split_block(unit, tiles, n_clusters, total, sb)) return;
   const int rows = min(128, n_rows - rb * 128);
   const int d4 = d >> 2;
   const float m = out_mul ? __ldg(out_mul) : 1.f;
@@ -864,11 +874,11 @@ __global__ void dx_reduce_kernel(const float* __restrict__ part, int n_clusters,
   for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < rows * d4; i += gridDim.y * blockDim.x) {
     const int r = i / d4, c4 = i - r * d4;
     const size_t off = (size_t)r * d4 + c4;
-    float4 a = part4[(size_t)(sb.c_first * 2 + sb.first_slot) * blk4 + off];
+    float4 a = part4[(size_t)((sb.c_first * 2 + sb.first_slot) * rpu + sub) * blk4 + off];
     for (int c = sb.c_first + 1; c <= sb.c_last; ++c) {
       int slot;
       if (!split_source(sb, c, n_clusters, total, slot)) continue;
-      const float4 b = part4[(size_t)(c * 2 + slot) * blk4 + off];
+      const float4 b = part4[(size_t)((c * 2 + slot) * rpu + sub) * blk4 + off];
       a.x += b.x;
       a.y += b.y;
       a.z += b.z;
@@ -929,7 +939,9 @@ static int plan_clusters(int n_row_blocks, int total_tiles) {
 }
 
 static size_t grad_ws_bytes(int n_rows, int n_cols, int d) {
-  const size_t nrb = (n_rows + 127) / 128, nt = (n_cols + 127) / 128;
+  // (row statistics are padded to whole row-block PAIRS: the quad kernel reads one block past an
+  // odd row-block count)
+  const size_t nrb = ((n_rows + 255) / 256) * 2, nt = (n_cols + 127) / 128;
   const size_t max_pairs = 74;   // sized for a whole B200 whatever the current SM limit
   const size_t partials = align256(max_pairs * 2 * 128 * (size_t)d * 4);
   return 3 * align256(nrb * 128 * 4) + 3 * align256(nt * 128 * 4) + align256(max_pairs * SMX_WARPS * 4) +
@@ -983,8 +995,50 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
     return fail(-1, "grad: the ping-pong experiment build needs two S buffers (d <= 512)");
   p.total_tiles = (n_cols + 127) / 128;
   p.n_row_blocks = (n_rows + 127) / 128;
+#ifdef VLP_BWD_QUAD
+  // quad kernel: units of two row blocks on clusters of four CTAs; as many clusters as can be
+  // co-resident (a GPC whose SM count is not a multiple of 4 strands SMs), never more
+  if (d % 128 != 0 || d > 512)
+    return fail(-1, "grad: the quad experiment build needs d %% 128 == 0 and d <= 512 (got %d)", d);
+  constexpr int kRpu = 2;
+  const int n_units = (p.n_row_blocks + 1) / 2;
+  int clusters;
+  {
+    constexpr size_t kRole = (size_t)P_RING_BYTES > (size_t)C_RING_BYTES + EPI_STAGE_BYTES
+                                 ? (size_t)P_RING_BYTES : (size_t)C_RING_BYTES + EPI_STAGE_BYTES;
+    const size_t smem_q = G_SLOTS * G_SLOT_BYTES + BAR_BYTES + kRole + 1024;
+    static int max_clusters = 0;
+    if (!max_clusters) {
+      VLP_CUDA_OK(cudaFuncSetAttribute(grad_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_q));
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3((usable_sms() / 4) * 4);
+      qc.blockDim = dim3(BWD_THREADS);
+      qc.dynamicSmemBytes = smem_q;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 4;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int n = 0;
+      VLP_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, grad_quad_kernel, &qc));
+      if (n <= 0) return fail(-2, "grad: no 4-CTA cluster of the quad kernel fits on this device");
+      max_clusters = n;
+    }
+    const long long total_q = (long long)n_units * p.total_tiles;
+    int want = usable_sms() / 4;
+    if (want > max_clusters) want = max_clusters;
+    clusters = total_q < want ? (int)total_q : want;
+  }
+  if (clusters * 2 > 74) return fail(-1, "grad: %d SM quads exceed the workspace layout", clusters);
+#else
+  constexpr int kRpu = 1;
+  const int n_units = p.n_row_blocks;
   const int clusters = plan_clusters(p.n_row_blocks, p.total_tiles);
   if (clusters > 74) return fail(-1, "grad: %d SM pairs exceed the workspace layout", clusters);
+#endif
   p.diag_shift = diag_shift;
   p.w_row = w_row;
   p.w_col = w_col;
@@ -994,7 +1048,7 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   p.out_scale = 1.0f / (2.0f * (float)n_global) / G_SCALE;
 
   uint8_t* ws = (uint8_t*)workspace;
-  const int npx = p.n_row_blocks * 128, npy = p.total_tiles * 128;
+  const int npx = ((p.n_row_blocks + 1) / 2) * 256, npy = p.total_tiles * 128;   // whole row-block pairs
   float* xmax = (float*)ws;
   ws += align256((size_t)npx * 4);
   float* xlg = (float*)ws;
@@ -1047,6 +1101,11 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   if (rc) return rc;
   rc = make_tmap_sw128(&map_mn, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, C_Q_PER_STAGE);
   if (rc) return rc;
+#ifdef VLP_BWD_QUAD
+  CUtensorMap map_p64;   // producers of the quad kernel: [64 q x 64 k] boxes (consumers use map_k's)
+  rc = make_tmap_sw128(&map_p64, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 64);
+  if (rc) return rc;
+#endif
 
   static_assert(sizeof(BwdBarriers) <= BAR_BYTES, "barrier block");
   constexpr size_t kRoleBytes = (size_t)P_RING_BYTES > (size_t)C_RING_BYTES + EPI_STAGE_BYTES
@@ -1070,7 +1129,11 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
     p.db0 = pass * per_pass;
     p.ndb = (p.kblocks - p.db0) < per_pass ? (p.kblocks - p.db0) : per_pass;
     p.ds_part = pass == 0 ? ds_keep : nullptr;
+#ifdef VLP_BWD_QUAD
+    grad_quad_kernel<<<clusters * 4, BWD_THREADS, smem, stream>>>(map_p64, map_k, p);
+#else
     grad_pair_kernel<<<clusters * 2, BWD_THREADS, smem, stream>>>(map_k, map_mn, p);
+#endif
     VLP_COUNT_LAUNCH(1);
   }
   if (kt.enabled) {
@@ -1080,13 +1143,13 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
   {
     // (a no-op for row blocks swept by a single cluster)
     dx_reduce_kernel<<<dim3(p.n_row_blocks, RED_SPLIT), 256, 0, stream>>>(
-        dx_part, clusters, p.n_row_blocks, p.total_tiles, n_rows, d, out_mul, dx_bf16, dx, p.scatter);
+        dx_part, clusters, n_units, p.total_tiles, n_rows, d, out_mul, dx_bf16, dx, p.scatter, kRpu);
     VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
   }
   if (dscale) {
-    ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, clusters * SMX_WARPS, 1.0f / (2.0f * (float)n_global),
-                                            dscale);
+    ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, clusters * kRpu * SMX_WARPS,
+                                            1.0f / (2.0f * (float)n_global), dscale);
   VLP_COUNT_LAUNCH(1);
     VLP_CUDA_OK(cudaGetLastError());
   }
