@@ -186,7 +186,8 @@ def one(name, n, d):
     if used.any():
         tiles = tiles_total / int(used.sum())
         tp, tc = b[used, 12].mean().item(), b[used, 13].mean().item()
-        print(f"[{name}]   bwd cycles/tile: producer {tp / tiles:.0f}, consumer {tc / tiles:.0f}")
+        print(f"[{name}]   bwd: {int(used.sum())} clusters, cycles/tile: producer {tp / tiles:.0f}, "
+              f"consumer {tc / tiles:.0f}")
         for i, nm in enumerate(BWD_NAMES):
             print(f"[{name}]     {nm:34s} {b[used, i].mean().item() / tiles:8.0f} cyc/tile")
     f = prof[74 * 16:].view(148, 8).double().cpu()
