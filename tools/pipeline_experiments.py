@@ -49,6 +49,7 @@ VARIANTS = {
     "g3": ("real", ["VLP_G_SLOTS=3"], "three G slots (consumer ring 3 x 32 KB): looser producer/consumer coupling"),
     "g3_push4_fine": ("real", ["VLP_G_SLOTS=3", "VLP_PUSH_SPLIT=4", "VLP_P_KB_PER_STAGE=1", "VLP_C_Q_PER_STAGE=32",
                                "VLP_FWD_KB_PER_STAGE=1"], "three G slots + split push + 16 KB ring stages"),
+    "epi8": ("real", ["VLP_EPI_WARPS=8"], "all 8 non-issuing consumer warps flush the accumulator (half the columns each)"),
     "no_smx": ("mock", ["VLP_EXP_NO_SMX", "VLP_EXP_NO_SMX_F"], "softmax arithmetic removed (fwd + bwd)"),
     "bwd_decouple": ("mock", ["VLP_EXP_DECOUPLE"], "no G hand-off: each backward role at its own pace"),
     "bwd_decouple_half_y": ("mock", ["VLP_EXP_DECOUPLE", "VLP_EXP_HALF_Y_P", "VLP_EXP_HALF_Y_C"],

@@ -113,7 +113,14 @@ static_assert(P_KB_PER_STAGE == 1 || P_KB_PER_STAGE == 2 || P_KB_PER_STAGE == 4,
 static_assert(C_Q_PER_STAGE == 32 || C_Q_PER_STAGE == 64, "consumer stage");
 constexpr int G_SLOT_BYTES = 32768;         // [128 rows x 128 q] fp16
 constexpr int BAR_BYTES = 1024;               // barrier block
-constexpr int EPI_STAGE_BYTES = 4 * 4096;    // consumer epilogue: one 32 x 32 fp32 tile per warp
+#ifndef VLP_EPI_WARPS
+#define VLP_EPI_WARPS 4
+#endif
+constexpr int EPI_WARPS = VLP_EPI_WARPS;     // consumer epilogue warps: 4, or all 8 non-issuing warps
+                                             // (two per TMEM lane quarter, half of the columns each)
+static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps");
+constexpr int EPI_PARTS = EPI_WARPS / 4;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 4096;   // one swizzled 32 x 32 fp32 tile per warp
 constexpr uint32_t BWD_TMEM_X = 0;          // producer: X block (fp16 packed), d/2 columns
 // producer S buffers (128 columns each) at the top of TMEM: two while d <= 512, one for d <= 768
 constexpr float G_SCALE = 8192.f;           // 2^13: keeps softmax tails out of fp16 subnormals
@@ -351,7 +358,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
     mbar_init(smem_u32(&bars->x_ready), 8);
     mbar_init(smem_u32(&bars->x_free), 1);
     mbar_init(smem_u32(&bars->acc_full), 1);
-    mbar_init(smem_u32(&bars->acc_free), 4);
+    mbar_init(smem_u32(&bars->acc_free), EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<1>(smem_u32(&bars->tmem_base), 512);
@@ -668,7 +675,7 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         if (elect_one()) umma_commit<1>(smem_u32(&bars->acc_full));
         __syncwarp();
       }
-    } else if (warp < 6) {
+    } else if (warp < 2 + EPI_WARPS) {
       // ---- epilogue: TMEM accumulator -> global ----
       const uint32_t quarter = warp & 3;
       const uint32_t lane_addr = (quarter * 32u) << 16;
@@ -704,7 +711,9 @@ grad_pair_kernel(const __grid_constant__ CUtensorMap map_y_k,   // box {64 k, 12
         const bool as_bf16 = final_out && p.dx_bf16;
         const uint32_t stg = stage + (warp - 2) * 4096;
         const int cbase = p.db0 * 64;   // first dX column of this pass
-        for (int cc = 0; cc < p.ndb * 64; cc += 32) {
+        const int cc_per = p.ndb * 64 / EPI_PARTS;          // columns of this warp's share
+        const int cc0 = (int)((warp - 2) >> 2) * cc_per;
+        for (int cc = cc0; cc < cc0 + cc_per; cc += 32) {
           uint32_t v[32];
           tmem_ld_x32(tmem + lane_addr + cc, v);
           tmem_ld_wait();

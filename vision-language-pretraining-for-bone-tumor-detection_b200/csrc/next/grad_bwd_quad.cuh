@@ -91,7 +91,7 @@ grad_quad_kernel(const __grid_constant__ CUtensorMap map_p,   // box {64 k, 64 q
     mbar_init(smem_u32(&bars->x_ready), 2 * 8);
     mbar_init(smem_u32(&bars->x_free), 1);
     mbar_init(smem_u32(&bars->acc_full), 1);
-    mbar_init(smem_u32(&bars->acc_free), 2 * 4);
+    mbar_init(smem_u32(&bars->acc_free), 2 * EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<2>(smem_u32(&bars->tmem_base), 512);   // both CTAs of each MMA pair
@@ -402,7 +402,7 @@ grad_quad_kernel(const __grid_constant__ CUtensorMap map_p,   // box {64 k, 64 q
             __syncwarp();
           }
       }
-    } else if (warp < 6) {
+    } else if (warp < 2 + EPI_WARPS) {
       // ---- epilogue (both consumers): own TMEM accumulator -> global ----
       const uint32_t quarter = warp & 3;
       const uint32_t lane_addr = (quarter * 32u) << 16;
@@ -436,7 +436,9 @@ grad_quad_kernel(const __grid_constant__ CUtensorMap map_p,   // box {64 k, 64 q
         const bool as_bf16 = final_out && p.dx_bf16;
         const uint32_t stg = stage + (warp - 2) * 4096;
         const int cbase = p.db0 * 64;
-        for (int cc = 0; cc < p.ndb * 64; cc += 32) {
+        const int cc_per = p.ndb * 64 / EPI_PARTS;          // columns of this warp's share
+        const int cc0 = (int)((warp - 2) >> 2) * cc_per;
+        for (int cc = cc0; cc < cc0 + cc_per; cc += 32) {
           uint32_t v[32];
           tmem_ld_x32(tmem + lane_addr + cc, v);
           tmem_ld_wait();
