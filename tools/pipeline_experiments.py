@@ -50,6 +50,8 @@ VARIANTS = {
     "g3_push4_fine": ("real", ["VLP_G_SLOTS=3", "VLP_PUSH_SPLIT=4", "VLP_P_KB_PER_STAGE=1", "VLP_C_Q_PER_STAGE=32",
                                "VLP_FWD_KB_PER_STAGE=1"], "three G slots + split push + 16 KB ring stages"),
     "epi8": ("real", ["VLP_EPI_WARPS=8"], "all 8 non-issuing consumer warps flush the accumulator (half the columns each)"),
+    "x_unroll": ("real", ["VLP_X_UNROLL"], "X block of a segment / work item fetched with all loads in flight (d = 512)"),
+    "x_unroll_epi8": ("real", ["VLP_X_UNROLL", "VLP_EPI_WARPS=8"], "both per-segment savings together"),
     "no_smx": ("mock", ["VLP_EXP_NO_SMX", "VLP_EXP_NO_SMX_F"], "softmax arithmetic removed (fwd + bwd)"),
     "bwd_decouple": ("mock", ["VLP_EXP_DECOUPLE"], "no G hand-off: each backward role at its own pace"),
     "bwd_decouple_half_y": ("mock", ["VLP_EXP_DECOUPLE", "VLP_EXP_HALF_Y_P", "VLP_EXP_HALF_Y_C"],

@@ -208,6 +208,28 @@ grad_quad_kernel(const __grid_constant__ CUtensorMap map_p,   // box {64 k, 64 q
           const int k_begin = grp * (dp / 2);
           const uint4* src =
               reinterpret_cast<const uint4*>(p.x + (size_t)(row_ok ? row : 0) * p.ldx);
+          if (kXUnroll && dp == 512) {
+            // all 32 loads of the thread's half row in flight at once: one L2 round trip instead of
+            // eight dependent ones while the tensor pipe waits for the new X block
+            uint4 w[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int k = k_begin + q * 8;
+              w[q] = (row_ok && k < p.d) ? __ldg(src + (k >> 3)) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              uint32_t v[16];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[q * 4 + 0] = w[g * 4 + q].x;
+                v[q * 4 + 1] = w[g * 4 + q].y;
+                v[q * 4 + 2] = w[g * 4 + q].z;
+                v[q * 4 + 3] = w[g * 4 + q].w;
+              }
+              tmem_st_x16(tmem + lane_addr + BWD_TMEM_X + k_begin / 2 + g * 16, v);
+            }
+          } else
           for (int c0 = 0; c0 < dp / 4; c0 += 16) {
             uint32_t v[16];
 #pragma unroll

@@ -40,6 +40,11 @@ constexpr int kFwdBoxDiv = 2;
 #else
 constexpr int kFwdBoxDiv = 1;
 #endif
+#ifdef VLP_X_UNROLL       // real variant: X block fetched with all loads in flight
+constexpr bool kFwdXUnroll = true;
+#else
+constexpr bool kFwdXUnroll = false;
+#endif
 #ifdef VLP_EXP_NO_SMX_F
 constexpr bool kFwdNoSoftmax = true;
 #else
@@ -278,6 +283,21 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       {
         const int k_begin = cg * (dp / FWD_CG);    // this thread's share of the row: dp/4 elements
         const uint4* src = reinterpret_cast<const uint4*>(p.x + (size_t)(row_ok ? row : 0) * p.ldx);
+        if (kFwdXUnroll && dp == 512) {
+          // all 16 loads of the thread's quarter row in flight at once (one L2 round trip, not eight)
+          uint4 w[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int k = k_begin + q * 8;
+            w[q] = (row_ok && k < p.d) ? __ldg(src + (k >> 3)) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            uint32_t v[8] = {w[2 * g].x, w[2 * g].y, w[2 * g].z, w[2 * g].w,
+                             w[2 * g + 1].x, w[2 * g + 1].y, w[2 * g + 1].z, w[2 * g + 1].w};
+            tmem_st_x8(tmem + lane_addr + TMEM_X_COL + k_begin / 2 + g * 8, v);
+          }
+        } else
         for (int c0 = 0; c0 < dp / (2 * FWD_CG); c0 += 8) {
           uint32_t v[8];
 #pragma unroll
