@@ -77,7 +77,7 @@ def next_sources():
 
 
 def build(only_missing=False):
-    """Cross-compile every variant (8 nvcc processes at a time)."""
+    """Cross-compile every variant (one nvcc process per core)."""
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(VAR_DIR, exist_ok=True)
 
@@ -89,7 +89,7 @@ def build(only_missing=False):
         return name
 
     todo = [n for n in VARIANTS if not (only_missing and os.path.exists(lib_of(n)))]
-    with ThreadPoolExecutor(max_workers=8) as ex:
+    with ThreadPoolExecutor(max_workers=max(1, min(len(todo) or 1, os.cpu_count() or 8))) as ex:
         for name in ex.map(one_build, todo):
             print("built", lib_of(name), flush=True)
 
