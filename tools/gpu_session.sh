@@ -14,4 +14,4 @@ timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_shipped.jso
 tail -c 600 gpurun_out/bench_shipped.json | tee -a gpurun_out/session.log
 echo "== staged variants (csrc/next): parity, kernel times, wait profiles" | tee -a gpurun_out/session.log
 timeout 1200 python tools/pipeline_experiments.py run "$N" "$D" > gpurun_out/pipeline_experiments.stdout 2>&1
-grep -E "parity|fwd rows-only|TIMEOUT|rc=" gpurun_out/pipeline_experiments.txt | tee -a gpurun_out/session.log
+grep -E "parity|fwd rows-only|rank shape|TIMEOUT|rc=" gpurun_out/pipeline_experiments.txt | tee -a gpurun_out/session.log

@@ -61,6 +61,7 @@ BWD_NAMES = ["P.tma  wait ring slot free", "P.mma  wait X staged", "P.mma  wait 
              "P.mma  wait Y stage full", "P.smx  wait X block released", "P.smx  wait S tile ready",
              "P.smx  wait G slot free", "P.smx  wait staging barrier", "C.tma  wait ring slot free",
              "C.mma  wait accumulator flushed", "C.mma  wait G tile arrived", "C.mma  wait Y stage full"]
+RECT_ROWS = (4096, 8192)   # rows per rank at 8 / 4 GPUs of the 32768-pair job
 FWD_NAMES = ["F.tma  wait ring slot free", "F.mma  wait X staged", "F.mma  wait S buffer free",
              "F.mma  wait Y stage full", "F.smx  wait X block released", "F.smx  wait S tile ready",
              "F.smx  wait column barrier"]
@@ -200,6 +201,28 @@ def one(name, n, d):
         print(f"[{name}]   fwd (fused) cycles/tile (incl. wave quantisation): {f[used, 7].mean().item() / tiles:.0f}")
         for i, nm in enumerate(FWD_NAMES):
             print(f"[{name}]     {nm:34s} {f[used, i].mean().item() / tiles:8.0f} cyc/tile")
+
+    # per-rank shapes of the sharded run on ONE GPU: R local rows against all n columns (rank 0's
+    # block), i.e. the three sweeps one rank of an (n / R)-GPU job executes
+    for R in RECT_ROWS:
+        if R >= n:
+            continue
+        Il, il16 = I[:R], i16[:R]
+        ms_f = timed(lambda: VF.lse_stats_fused(Il, T, s, 0))
+        rm, rl, rdiag, cm, cl = VF.lse_stats_fused(Il, T, s, 0)
+        cdiag = torch.zeros(n, dtype=torch.float32, device=dev)
+        cdiag[:R] = rdiag
+        rr, cc = VF.merge_stats(rm, rl, rdiag, s)[:3], VF.merge_stats(cm, cl, cdiag, s)[:3]
+        lib.vlpclip_time_grad_kernel(1)
+        ms_di = ms_dt = 1e9
+        for _ in range(3):
+            VF._grad(il16, t16, rr, cc, s, 0, n, 1.0, 1.0, True)
+            ms_di = min(ms_di, lib.vlpclip_last_grad_kernel_ms())
+            VF._grad(t16, il16, cc, rr, s, 0, n, 1.0, 1.0, True)
+            ms_dt = min(ms_dt, lib.vlpclip_last_grad_kernel_ms())
+        lib.vlpclip_time_grad_kernel(0)
+        print(f"[{name}] rank shape {R} x {n} ({n // R} GPUs): fwd fused {ms_f * 1e3:.0f} us, "
+              f"dI kernel {ms_di * 1e3:.0f} us, dT kernel {ms_dt * 1e3:.0f} us")
 
 
 def run(n, d):
