@@ -1,4 +1,4 @@
-"""CPU, gloo, world_size 2 and 4: the sharded plan (all-gather / partial-stat merge / all-reduce /
+"""CPU, gloo, world_size 2, 4 and 8 (one NVSwitch box): the sharded plan (all-gather / partial-stat merge / all-reduce /
 reduce-scatter orchestration of vlp_b200.sharded) against the single-process oracle."""
 import math
 import os
@@ -77,7 +77,7 @@ def test_sharded_plan_matches_single_process_oracle(tmp_path, world, n, d, ls, e
         assert abs(float(got["ds"][0]) - ref["dscale"]) < 1e-10 * max(1.0, abs(ref["dscale"]))
 
 
-@pytest.mark.parametrize("world,n,d,ls", [(2, 96, 32, 2.6593), (4, 64, 16, 3.5)])
+@pytest.mark.parametrize("world,n,d,ls", [(2, 96, 32, 2.6593), (4, 64, 16, 3.5), (8, 64, 16, 2.6593)])
 def test_sharded_plan_with_peer_window_ops_matches_oracle(tmp_path, world, n, d, ls):
     """Same check through the fused-collective branches (push-gather, row scatter into owner slots,
     slot sum in rank order, upstream gradient applied by the finishing op)."""

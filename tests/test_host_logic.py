@@ -174,3 +174,22 @@ def test_retrieval_metrics_match_reference_semantics():
         assert abs(a[k] - b[k]) < 1e-6 and abs(c[k] - d[k]) < 1e-9
     with pytest.raises(AssertionError):
         precision_at_k_on_image_embeddings(img[:10], labels[:10], [15])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: one JSON line on stdout with the driver's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--n", "2048", "--cpu-block", "128"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["value"] > 0 and line["config"]["global_batch"] == 2048
