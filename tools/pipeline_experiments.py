@@ -31,6 +31,9 @@ VARIANTS = {
     "base": ("real", [], "staged kernels without switches (= shipped algorithms) + wait counters"),
     "bwd_pingpong": ("real", ["VLP_BWD_PINGPONG"],
                      "softmax warp groups alternate whole tiles (2 tile times per tile and group)"),
+    "fwd_pingpong": ("real", ["VLP_FWD_PINGPONG"],
+                     "forward softmax warps as two groups of 8 alternating whole tiles (two 32-column passes each)"),
+    "fwd_pair_pingpong": ("real", ["VLP_FWD_PAIR", "VLP_FWD_PINGPONG"], "both forward variants together"),
     "fwd_pair": ("real", ["VLP_FWD_PAIR"],
                  "forward on CTA pairs with cta_group::2 MMAs: each SM stages half of every Y tile"),
     "bwd_quad": ("real", ["VLP_BWD_QUAD"],

@@ -45,6 +45,13 @@ constexpr bool kFwdXUnroll = true;
 #else
 constexpr bool kFwdXUnroll = false;
 #endif
+#ifdef VLP_FWD_PINGPONG   // real variant: the softmax warps form two groups of 8 that alternate whole S
+constexpr bool kFwdPingPong = true;   // tiles (group g = tile parity = S buffer); a thread walks 64 columns
+#else                                 // of its row in two 32-column passes -> a group has two tile times
+constexpr bool kFwdPingPong = false;  // for the latency chain ld -> max -> ex2 -> butterfly -> combine
+#endif
+constexpr int FWD_PASSES = kFwdPingPong ? 2 : 1;
+constexpr int FWD_TILE_WARPS = kFwdPingPong ? 8 : 16;   // softmax warps that share one S tile
 #ifdef VLP_EXP_NO_SMX_F
 constexpr bool kFwdNoSoftmax = true;
 #else
@@ -124,7 +131,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->s_empty[i]), FWD_SMW * CG);  // one arrive per softmax warp
+      mbar_init(smem_u32(&bars->s_empty[i]), FWD_TILE_WARPS * CG);  // one arrive per softmax warp of the tile
     }
     mbar_init(smem_u32(&bars->x_ready), FWD_SMW * CG);
     mbar_init(smem_u32(&bars->x_free), 1);
@@ -253,6 +260,8 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     const uint32_t quarter = warp & 3;
     const uint32_t wslot = warp - 2;             // 0 .. FWD_SMW-1
     const uint32_t cg = wslot >> 2;
+    const uint32_t grp = wslot >> 3;             // ping-pong: tile parity this warp works on
+    const uint32_t chalf = cg & 1;               // ping-pong: 64-column half of the tile
     const uint32_t row_in_blk = quarter * 32 + lane;
     const uint32_t lane_addr = (quarter * 32u) << 16;
     const int dp = p.kblocks * 64;               // padded K
@@ -322,6 +331,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       // column holding this row's positive pair (none for padded rows)
       const int dcol = row_ok ? row - p.diag_shift : -1000000000;
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
+        if (kFwdPingPong && (tile_ctr & 1) != grp) continue;   // the other group's tile
         const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
         const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
         if (CG == 2)
@@ -329,18 +339,23 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         else
           VLP_WAIT(5, mbar_wait(smem_u32(&bars->s_full[buf]), use & 1));
         tc_fence_after();
+#pragma unroll 1
+       for (int pass = 0; pass < FWD_PASSES; ++pass) {
+        const uint32_t colgrp = kFwdPingPong ? chalf * 2 + (uint32_t)pass : cg;   // 32-column group
         uint32_t v[FWD_CPT];
-        tmem_ld_x32(tmem + lane_addr + tmem_s_col + buf * 128 + cg * FWD_CPT, v);
+        tmem_ld_x32(tmem + lane_addr + tmem_s_col + buf * 128 + colgrp * FWD_CPT, v);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive_leader(&bars->s_empty[buf]);
+        if (pass == FWD_PASSES - 1) {   // tile fully read: the MMA warp may overwrite the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader(&bars->s_empty[buf]);
+        }
         if (kFwdNoSoftmax) {   // timing mock: keep the loads observable, skip the arithmetic
           mraw_run = fmaxf(mraw_run, __uint_as_float(v[lane & (FWD_CPT - 1)]));
           continue;
         }
 
-        const int col0 = t * 128 + cg * FWD_CPT;
+        const int col0 = t * 128 + colgrp * FWD_CPT;
         // columns past n_cols were zero-filled by TMA: mask them out of the statistics
         if (col0 + FWD_CPT > p.n_cols) {
 #pragma unroll
@@ -406,32 +421,45 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
               c[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
             }
           }
-          const uint32_t par = tile_ctr & 1;
-          bars->col_s[par][wslot][lane] = c[0];
-          if (lane == 0) bars->col_r[par][wslot] = R - COL_HEADROOM;
-          VLP_WAIT(6, bar_sync(2, FWD_SMW * 32));
-          const uint32_t st = wslot * 32 + lane;   // the first 128 softmax threads own one column
-          if (st < 128 && (CG == 1 || rb < p.n_row_blocks)) {   // pair: skip a phantom row block
-            const uint32_t g = st >> 5, cc = st & 31;   // warps of column group g: slots g*4 .. g*4+3
+          // the four lane quarters of a 32-column group meet through shared memory.  Slots:
+          //   default    [tile parity][wslot]: 16 warps = 4 column groups x 4 quarters, one barrier
+          //   ping-pong  [group][pass * 8 + warp in group]: per pass the group's 8 warps = 2 column
+          //              groups x 4 quarters; a group's own barrier (its warps only)
+          const uint32_t par = tile_ctr & 1;            // = grp in ping-pong mode
+          const uint32_t myslot = kFwdPingPong ? (uint32_t)pass * 8 + (wslot & 7) : wslot;
+          bars->col_s[par][myslot][lane] = c[0];
+          if (lane == 0) bars->col_r[par][myslot] = R - COL_HEADROOM;
+          VLP_WAIT(6, bar_sync(kFwdPingPong ? 2 + grp : 2, FWD_TILE_WARPS * 32));
+          // combining threads: one per column handled in this pass (128, or 64 in ping-pong mode)
+          const uint32_t st = (kFwdPingPong ? (wslot & 7) : wslot) * 32 + lane;
+          if (st < (kFwdPingPong ? 64u : 128u) && (CG == 1 || rb < p.n_row_blocks)) {   // pair: skip a phantom row block
+            const uint32_t g = st >> 5, cc = st & 31;
+            // slots of the 4 quarters of that column group, and the group's first column in the tile
+            const uint32_t s0 = kFwdPingPong ? (uint32_t)pass * 8 + g * 4 : g * 4;
+            const uint32_t cgrp = kFwdPingPong ? g * 2 + (uint32_t)pass : g;
             float r4[4], l4[4], M = -INFINITY;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              r4[q] = bars->col_r[par][g * 4 + q];
-              l4[q] = bars->col_s[par][g * 4 + q][cc];
+              r4[q] = bars->col_r[par][s0 + q];
+              l4[q] = bars->col_s[par][s0 + q][cc];
               M = fmaxf(M, r4[q]);
             }
             float l = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               if (r4[q] != -INFINITY) l += l4[q] * ex2_approx(r4[q] - M);
-            const size_t o = (size_t)rb * ((size_t)p.total_tiles * 128) + (size_t)t * 128 + st;
+            const size_t o = (size_t)rb * ((size_t)p.total_tiles * 128) + (size_t)t * 128 +
+                             cgrp * FWD_CPT + cc;
             p.col_ref[o] = M;
             p.col_l[o] = l;
           }
         }
+       }   // pass
       }
       if (row_ok) {
-        const size_t o = (size_t)(chunk * FWD_CG + cg) * p.n_rows + row;
+        // (ping-pong: the four partials of a row are (group, column half) instead of column groups)
+        const uint32_t part_idx = kFwdPingPong ? grp * 2 + chalf : cg;
+        const size_t o = (size_t)(chunk * FWD_CG + part_idx) * p.n_rows + row;
         p.part_m[o] = mraw_run;
         p.part_l[o] = l_run;
       }
@@ -724,6 +752,8 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   p.kblocks = (d + 63) / 64;
   p.total_tiles = (n_cols + 127) / 128;
   p.n_row_blocks = (n_rows + 127) / 128;
+  if (kFwdPingPong && p.kblocks > 8)
+    return fail(-1, "lse_fwd: the ping-pong experiment build needs two S buffers (d <= 512)");
   const int nsm = usable_sms();
 #ifdef VLP_FWD_PAIR
   constexpr int kFwdCG = 2;   // experiment build: cta_group::2 forward (tools/pipeline_experiments.py)
