@@ -14,6 +14,7 @@ pass, plus the blocked-cycle profile of every pipeline role (all variants carry
                                                                 does not travel with gpurun -- and writes
                                                                 gpurun_out/pipeline_experiments.txt)
     python tools/pipeline_experiments.py one <name> [N] [D]    (B200; one variant, this process)
+    VARIANTS=base,bwd_quad python tools/pipeline_experiments.py run   (a subset)
 """
 import math
 import os
@@ -233,7 +234,11 @@ def run(n, d):
     os.makedirs(out_dir, exist_ok=True)
     log = open(os.path.join(out_dir, "pipeline_experiments.txt"), "w")
     build(only_missing=True)   # tools/variants/ is gpurun-ignored: missing libraries are built on the box
-    for name in VARIANTS:
+    only = [v for v in os.environ.get("VARIANTS", "").split(",") if v]   # optional subset, e.g. VARIANTS=base,bwd_quad
+    for name in (only or VARIANTS):
+        if name not in VARIANTS:
+            sys.stdout.write(f"[{name}] unknown variant\n")
+            continue
         if not os.path.exists(lib_of(name)):
             line = f"[{name}] library missing: run `python tools/pipeline_experiments.py build` first\n"
         else:
