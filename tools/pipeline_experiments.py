@@ -81,7 +81,7 @@ def next_sources():
             os.path.join(_build.CSRC, "prologue.cu")]
 
 
-def build(only_missing=False):
+def build(only_missing=False, names=None):
     """Cross-compile every variant (one nvcc process per core)."""
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(VAR_DIR, exist_ok=True)
@@ -93,7 +93,7 @@ def build(only_missing=False):
         subprocess.run(cmd, check=True)
         return name
 
-    todo = [n for n in VARIANTS if not (only_missing and os.path.exists(lib_of(n)))]
+    todo = [n for n in (names or VARIANTS) if n in VARIANTS and not (only_missing and os.path.exists(lib_of(n)))]
     with ThreadPoolExecutor(max_workers=max(1, min(len(todo) or 1, os.cpu_count() or 8))) as ex:
         for name in ex.map(one_build, todo):
             print("built", lib_of(name), flush=True)
@@ -233,8 +233,8 @@ def run(n, d):
     out_dir = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
     log = open(os.path.join(out_dir, "pipeline_experiments.txt"), "w")
-    build(only_missing=True)   # tools/variants/ is gpurun-ignored: missing libraries are built on the box
     only = [v for v in os.environ.get("VARIANTS", "").split(",") if v]   # optional subset, e.g. VARIANTS=base,bwd_quad
+    build(only_missing=True, names=only or None)   # tools/variants/ is gpurun-ignored: built on the box
     for name in (only or VARIANTS):
         if name not in VARIANTS:
             sys.stdout.write(f"[{name}] unknown variant\n")
