@@ -126,7 +126,7 @@ def test_staged_variants_compile_and_use_the_paired_forms(tmp_path):
 
     def compile_one(name):
         out = str(tmp_path / f"{name}.so")
-        cmd = [_build._nvcc()] + _build.NVCC_FLAGS + ["-DVLP_PROFILE_WAITS"] + \
+        cmd = [_build._nvcc()] + _build.NVCC_FLAGS + ["-DVLP_PROFILE_WAITS", "-DVLP_WAIT_WATCHDOG"] + \
               [f"-D{d}" for d in pe.VARIANTS[name][1]] + ["-o", out] + pe.next_sources()
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-2000:]

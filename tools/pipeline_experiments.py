@@ -6,7 +6,8 @@ tools/variants/libvlpclip_<name>.so -- the shipped library and its sources csrc/
 touched -- and, on a B200, runs every variant in its own process (a hung mock cannot take the
 others down): kernel times of the forward sweep (rows only / fused columns) and of one backward
 pass, plus the blocked-cycle profile of every pipeline role (all variants carry
--DVLP_PROFILE_WAITS).  Variants marked "real" are also checked against a torch fp32 reference;
+-DVLP_PROFILE_WAITS, and -DVLP_WAIT_WATCHDOG: a barrier wait of more than ~1 s traps instead of
+hanging the GPU).  Variants marked "real" are also checked against a torch fp32 reference;
 "mock" variants compute garbage by construction and are timing-only.
 
     python tools/pipeline_experiments.py build                 (cross-compile all variants; compile check)
@@ -88,7 +89,7 @@ def build(only_missing=False, names=None):
 
     def one_build(name):
         defs = VARIANTS[name][1]
-        cmd = [_build._nvcc()] + _build.NVCC_FLAGS + ["-DVLP_PROFILE_WAITS"] + [f"-D{d}" for d in defs] + \
+        cmd = [_build._nvcc()] + _build.NVCC_FLAGS + ["-DVLP_PROFILE_WAITS", "-DVLP_WAIT_WATCHDOG"] + [f"-D{d}" for d in defs] + \
               ["-o", lib_of(name)] + next_sources()
         subprocess.run(cmd, check=True)
         return name
@@ -244,7 +245,7 @@ def run(n, d):
         else:
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "one", name, str(n), str(d)],
-                                   capture_output=True, text=True, timeout=120)
+                                   capture_output=True, text=True, timeout=90)
                 line = r.stdout + ("" if r.returncode == 0 else f"[{name}] rc={r.returncode}\n{r.stderr[-2000:]}\n")
             except subprocess.TimeoutExpired:
                 line = f"[{name}] TIMEOUT (hung kernel?)\n"

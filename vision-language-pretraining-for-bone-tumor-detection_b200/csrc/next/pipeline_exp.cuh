@@ -32,4 +32,39 @@ inline long long*& wait_prof_buffer() {
   return p;
 }
 
+// -DVLP_WAIT_WATCHDOG (set for every experiment build): a barrier wait that lasts longer than 2^31
+// cycles (~1 s; a whole kernel takes milliseconds) reports itself and traps, so that a protocol bug
+// in a staged variant ends the process with an error instead of hanging the GPU.
+#ifdef VLP_WAIT_WATCHDOG
+VLP_DEVICE void wait_watchdog_fire(uint32_t bar, uint32_t parity, int cluster_scope) {
+  printf("VLP WATCHDOG: block %d thread %d (cluster rank %u) stuck on mbarrier smem+0x%x parity %u%s\n",
+         (int)blockIdx.x, (int)threadIdx.x, cluster_ctarank(), bar & 0xFFFFFFu, parity,
+         cluster_scope ? " (cluster-scope wait)" : "");
+  __trap();
+}
+VLP_DEVICE void mbar_wait_wd(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > (1ll << 31)) wait_watchdog_fire(bar, parity, 0);
+}
+VLP_DEVICE void mbar_wait_cluster_wd(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > (1ll << 31)) wait_watchdog_fire(bar, parity, 1);
+  }
+}
+#define mbar_wait mbar_wait_wd
+#define mbar_wait_cluster mbar_wait_cluster_wd
+#endif
+
 }  // namespace vlp
