@@ -55,6 +55,16 @@ def _worker(rank, world, port, n, d, ls, out_dir, exact, windows=False):
                  image_loss=plan["image_loss"].numpy(), text_loss=plan["text_loss"].numpy(),
                  dI=d_i.numpy(), dT=d_t.numpy(), ds=ds.numpy())
     finally:
+        # the emulated windows hold a reference to the process group: drop it before the group is
+        # destroyed, or the gloo backend is torn down at interpreter exit with its threads still
+        # joinable (sporadic "terminate called without an active exception" / SIGABRT)
+        try:
+            from kernel_contract_ops import WindowContractOps as _W
+            _W.windows.clear()
+        except Exception:
+            pass
+        import gc
+        gc.collect()
         dist.destroy_process_group()
 
 
