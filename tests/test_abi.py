@@ -142,3 +142,15 @@ def test_staged_variants_compile_and_use_the_paired_forms(tmp_path):
         for name in ("fwd_pair", "bwd_quad"):
             sass = subprocess.run([cuobjdump, "-sass", libs[name]], capture_output=True, text=True).stdout
             assert "UTCHMMA.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass, name
+
+
+def test_promotion_tool_dry_run_lists_the_files_it_would_write():
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "promote_next.py"), "--dry-run",
+                        "VLP_X_UNROLL", "VLP_EPI_WARPS=8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    for fn in ("variant_defaults.cuh", "lse_fwd.cu", "grad_bwd.cu", "grad_bwd_quad.cuh", "pipeline_exp.cuh"):
+        assert fn in r.stdout
+    bad = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "promote_next.py"), "--dry-run",
+                          "VLP_EXP_NO_SMX"], capture_output=True, text=True, timeout=300)
+    assert bad.returncode != 0      # timing mocks are never promoted
