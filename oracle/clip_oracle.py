@@ -31,7 +31,7 @@ Arithmetic lives in PyTorch itself (reference pins torch 2.7.0, this image has 2
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import logging
 from itertools import chain
-from typing import Dict, Optional, Sequence
+from typing import Dict, Sequence
 
 import numpy as np
 import torch

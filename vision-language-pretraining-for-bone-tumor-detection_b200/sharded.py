@@ -43,8 +43,6 @@ backward  dT rows stored into the owner's peer window from the kernel epilogue (
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 
 
