@@ -5,16 +5,19 @@
 // (reference: VisionLanguageModule.py:459 `logits = (I @ T.T) * logit_scale` and the
 // log-softmax half of F.cross_entropy at :550 / :551).
 //
-// Mapping to the SM (one persistent CTA per SM, 320 threads):
-//   warp 0      TMA producer: streams Y as [128 rows x 64 k] bf16 boxes (SW128) through an
-//               8-deep smem ring (16 KB per stage).
+// Mapping to the SM (one persistent CTA per SM, 576 threads):
+//   warp 0      TMA producer: streams Y as [128 rows x 64 k] bf16 boxes (SW128) through a
+//               192 KB smem ring (6 stages of two boxes).
 //   warp 1      tcgen05 issuer: S[128 x 128] (fp32, TMEM, double buffered) = X * Y_tile^T with the
 //               A operand (X row block, bf16 packed) RESIDENT IN TMEM (TS form: 74 cycles per
 //               K=16 step instead of 107 for the SS form -- see profiles/r01_probe_notes.md).
-//   warps 2..9  softmax: thread = (row, 64-column half); tcgen05.ld the S row, online max/sum in
-//               the log2 domain, one ex2 per logit.
-// Work item = (row block, chunk of column tiles); partial (m, l) pairs per (chunk, half) go to
-// a workspace and are merged by lse_merge_kernel in fixed order (bit reproducible).
+//   warps 2..17 softmax: thread = (row, 32-column group); tcgen05.ld the S row, online max/sum in
+//               the log2 domain, one ex2 per logit; with kCols the same ex2 values also feed the
+//               column statistics (warp butterfly over the 32 rows, quarters combined in smem).
+// Work item = (row block, chunk of column tiles); partial (m, l) pairs per (chunk, column group)
+// go to a workspace and are merged by lse_merge_kernel in fixed order (bit reproducible).
+// This is the STAGED version (csrc/next/): build-time switches select experiment variants
+// (ping-pong softmax groups, cta_group::2 pairs, ring geometry, timing mocks), see below.
 #include <cuda_bf16.h>
 #include "pipeline_exp.cuh"
 #include "../../../include/vlpclip.h"
