@@ -85,7 +85,9 @@ def _grad_plan(n_row_blocks, tiles, n_clusters):
 
 @pytest.mark.parametrize("shape", [(256, 256, 74), (2, 2, 74), (1, 1, 1), (32, 256, 72),
                                    (256, 32, 72), (3, 5, 4), (512, 512, 74), (7, 1, 3),
-                                   (1, 300, 74), (128, 256, 72), (5, 7, 74)])
+                                   (1, 300, 74), (128, 256, 72), (5, 7, 74),
+                                   # the staged quad kernel cuts (row-block PAIRS x tiles) over 4-CTA clusters
+                                   (128, 256, 37), (16, 256, 37), (128, 32, 37), (4, 8, 37), (128, 256, 33)])
 def test_backward_work_partition_is_exact_and_balanced(shape):
     """Every (row block, column tile) is swept exactly once, the load differs by <= 1 tile between
     SM pairs, each pair owns at most one head and one tail partial block, and the pieces the
