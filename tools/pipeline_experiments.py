@@ -48,6 +48,8 @@ VARIANTS = {
     "half_y_bwd_pc": ("mock", ["VLP_EXP_HALF_Y_P", "VLP_EXP_HALF_Y_C"], "both backward roles stream half of Y"),
     "fine_rings": ("real", ["VLP_P_KB_PER_STAGE=1", "VLP_C_Q_PER_STAGE=32", "VLP_FWD_KB_PER_STAGE=1"],
                    "16 KB ring stages everywhere (8 / 8 / 12 stages): fewer bytes pinned under the MMAs"),
+    "fine_p": ("real", ["VLP_P_KB_PER_STAGE=1"], "16 KB stages in the backward producer's ring only (8 stages)"),
+    "fine_c": ("real", ["VLP_C_Q_PER_STAGE=32"], "16 KB stages in the backward consumer's ring only (8 stages)"),
     "fine_rings_pingpong": ("real", ["VLP_P_KB_PER_STAGE=1", "VLP_C_Q_PER_STAGE=32", "VLP_FWD_KB_PER_STAGE=1",
                                      "VLP_BWD_PINGPONG"], "both real variants together"),
     "push4": ("real", ["VLP_PUSH_SPLIT=4"], "G tile pushed to the consumer as 4 concurrent 8 KB bulk copies"),
