@@ -173,6 +173,36 @@ int vlpclip_grad_scatter(const void* x_f16, int ldx, const void* y_f16, int ldy,
                          const float* scale, int diag_shift, int n_global, float w_row, float w_col,
                          void* const* owner_rows, int n_owners, int rows_per_owner, float* dscale,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* ---- single-recompute backward: dX, dY and dscale from ONE sweep over the logit tiles ----
+ * Same mathematics as two vlpclip_grad calls ((X, Y) and (Y, X)), but every tile of
+ * G = d loss / d S is formed once and feeds both accumulations (8 N^2 D executed flops per training
+ * step instead of 10 N^2 D):
+ *   dX[n_rows, d] = scale * G   Y   (rows of X; fp32 or bf16, multiplied by out_mul if given)
+ *   dY[n_cols, d] = scale * G^T X   (rows of Y; fp32 or bf16, multiplied by out_mul if given), or,
+ *                   when dy_owner_rows != NULL, stored fp32 without out_mul into the owning ranks'
+ *                   peer windows exactly like vlpclip_grad_scatter (fused reduce-scatter; dy ignored)
+ *   dscale        = sum_ij G_ij <X_i, Y_j>  (optional)
+ * Statistics, weights, diag_shift and n_global as for vlpclip_grad with (X, Y) in this order.
+ * Runs as ONE persistent kernel on all SMs (producer / dI-consumer SM pairs + dT-consumer SMs that
+ * exchange G tiles through an L2-resident ring inside the workspace); the sums are formed in a
+ * fixed order, so results are bit-reproducible.
+ * Replaces autograd of VisionLanguageModule.py:459, :550-552 (both embedding gradients at once). */
+size_t vlpclip_grad_both_workspace_bytes(int n_rows, int n_cols, int d);
+int vlpclip_grad_both(const void* x_f16, int ldx, const void* y_f16, int ldy, const float* x_max,
+                      const float* x_lg2l, const float* x_q, const float* y_max, const float* y_lg2l,
+                      const float* y_q, int n_rows, int n_cols, int d, const float* scale,
+                      int diag_shift, int n_global, float w_row, float w_col, const float* out_mul,
+                      int dx_bf16, void* dx, int dy_bf16, void* dy, void* const* dy_owner_rows,
+                      int n_owners, int rows_per_owner, float* dscale, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* host-only: the schedule of vlpclip_grad_both for np producer slots and nq >= np dT consumers
+ * (np <= 0: the split used on the current device).  info[8] = {phases, nominal steps, dI partial
+ * slots, runs, waves, np, nq, 0}; prod rows = {slot, step, row block, column tile, dI partial slot
+ * or -1}; cons rows = {consumer, slot, step, row block, column tile, rank of the piece in its
+ * column, pieces of the column} in the order each consumer works.  Used by the CPU test-suite. */
+int vlpclip_grad_both_plan(int n_row_blocks, int n_col_tiles, int np, int nq, int* info, int* prod,
+                           int max_prod, int* n_prod, int* cons, int max_cons, int* n_cons);
+
 /* out[slot_elems] (fp32 or bf16) = out_mul * sum_s slots[s * slot_elems + .], s ascending */
 int vlpclip_slot_sum(const float* slots, int n_slots, size_t slot_elems, const float* out_mul,
                      int out_bf16, void* out, void* stream);

@@ -111,48 +111,3 @@ def test_backward_work_partition_is_exact_and_balanced(shape):
     for rb in set(red[:, 0].tolist()):
         cls = red[red[:, 0] == rb][:, 1]
         assert (np.diff(cls) > 0).all()
-
-
-# ---- staged kernels (csrc/next/): must keep compiling for sm_100a with every switch --------------
-def test_staged_variants_compile_and_use_the_paired_forms(tmp_path):
-    """The experiment builds of tools/pipeline_experiments.py cross-compile (no GPU needed); the
-    cta_group::2 variants really issue 2-CTA MMAs and multicast commits."""
-    import importlib.util
-    from concurrent.futures import ThreadPoolExecutor
-    spec = importlib.util.spec_from_file_location(
-        "pipeline_experiments", os.path.join(ROOT, "tools", "pipeline_experiments.py"))
-    pe = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(pe)
-    names = ["bwd_pingpong", "g3_push4_fine", "fwd_pair", "bwd_quad"]
-    assert all(n in pe.VARIANTS for n in names)
-
-    def compile_one(name):
-        out = str(tmp_path / f"{name}.so")
-        cmd = [_build._nvcc()] + _build.NVCC_FLAGS + ["-DVLP_PROFILE_WAITS", "-DVLP_WAIT_WATCHDOG"] + \
-              [f"-D{d}" for d in pe.VARIANTS[name][1]] + ["-o", out] + pe.next_sources()
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        assert r.returncode == 0, r.stderr[-2000:]
-        return out
-
-    with ThreadPoolExecutor(max_workers=4) as ex:
-        libs = dict(zip(names, ex.map(compile_one, names)))
-    for lib_path in libs.values():   # same ABI as the shipped library
-        lib = ctypes.CDLL(lib_path)
-        assert not [f for f in header_functions() if not hasattr(lib, f)]
-    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
-    if os.path.exists(cuobjdump):
-        for name in ("fwd_pair", "bwd_quad"):
-            sass = subprocess.run([cuobjdump, "-sass", libs[name]], capture_output=True, text=True).stdout
-            assert "UTCHMMA.2CTA" in sass and "UTCBAR.2CTA.MULTICAST" in sass, name
-
-
-def test_promotion_tool_dry_run_lists_the_files_it_would_write():
-    import sys
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "promote_next.py"), "--dry-run",
-                        "VLP_X_UNROLL", "VLP_EPI_WARPS=8"], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stderr[-1500:]
-    for fn in ("variant_defaults.cuh", "lse_fwd.cu", "grad_bwd.cu", "grad_bwd_quad.cuh", "pipeline_exp.cuh"):
-        assert fn in r.stdout
-    bad = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "promote_next.py"), "--dry-run",
-                          "VLP_EXP_NO_SMX"], capture_output=True, text=True, timeout=300)
-    assert bad.returncode != 0      # timing mocks are never promoted

@@ -52,6 +52,13 @@ _SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                      c_int, c_int, c_float, c_float, c_void_p, c_int, c_int,
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlpclip_grad_both_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "vlpclip_grad_both": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                  c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlpclip_grad_both_plan": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                       c_void_p, c_void_p, c_int, c_void_p]),
     "vlpclip_slot_sum": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
     "vlpclip_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "vlpclip_peer_open": (c_int, [c_void_p, c_void_p]),

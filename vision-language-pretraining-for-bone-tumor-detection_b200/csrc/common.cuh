@@ -52,7 +52,7 @@ inline EncodeTiledFn get_encode_fn() {
 // Row-major [outer][inner] matrix of `elem_bytes`-wide elements, row stride `ld` elements.
 // Box = {128 B worth of inner elements, box_outer rows}, 128-byte swizzle, OOB reads give 0.
 inline int make_tmap_sw128(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner,
-                           uint64_t outer, uint64_t ld, uint32_t box_outer) {
+                           uint64_t outer, uint64_t ld, uint32_t box_outer, bool as_float32 = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(-3, "cuTensorMapEncodeTiled unavailable (driver too old?)");
   if ((reinterpret_cast<uintptr_t>(gptr) & 15) != 0)
@@ -64,7 +64,9 @@ inline int make_tmap_sw128(CUtensorMap* out, const void* gptr, int elem_bytes, u
   cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_outer};
   cuuint32_t estr[2] = {1, 1};
+  // (loads and stores only move bytes; the element type matters for TMA reduce-add)
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                           : as_float32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                            : CU_TENSOR_MAP_DATA_TYPE_UINT32;
   CUresult r = enc(out, dt, 2, const_cast<void*>(gptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -73,16 +75,33 @@ inline int make_tmap_sw128(CUtensorMap* out, const void* gptr, int elem_bytes, u
   return 0;
 }
 
+// per-device caches (a process may drive several GPUs)
+constexpr int kMaxDevices = 64;
 inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
-    n = p.multiProcessorCount;
+  static int n[kMaxDevices] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  if (!n[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per
+// (kernel slot, device).  `slot` is a small per-kernel index chosen by the caller.
+inline cudaError_t set_smem_attr_once(const void* fn, int bytes, int slot = 0) {
+  static unsigned char done[16][kMaxDevices] = {{0}};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (slot < 0 || slot >= 16 || dev < 0 || dev >= kMaxDevices)
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (done[slot][dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[slot][dev] = 1;
+  return e;
 }
 
 // optional cap on the SMs the persistent kernels occupy (0 = all): leaves room for NCCL kernels

@@ -1,0 +1,950 @@
+// grad_both.cuh -- single-recompute backward: ONE sweep over the logit tiles yields dI, dT and dscale
+// (8 N^2 D executed flops per step instead of the 10 N^2 D of two grad_pair_kernel passes).
+// Included by grad_bwd.cu inside namespace vlp, after the helpers it reuses.
+//
+//   dI_i += G(i,j)   T_j        dT_j += G(i,j)^T I_i        G = d loss / d S  (fp16, scaled by 2^13)
+//
+// Every G tile is formed once, by a PRODUCER SM (S tile with I_i resident in TMEM, TS-form MMAs, 16
+// softmax warps), staged in shared memory as a K-major / 128B-swizzled fp16 tile and written with
+// one 1-D bulk copy into a small ring in global memory (8 tiles per producer: 12.5 MB, L2
+// resident).  Two CONSUMER SMs fetch it from there with 1-D bulk copies (the byte image is
+// unchanged, so it matches their UMMA descriptors):
+//   * the dI consumer of producer slot a follows that producer tile by tile:
+//       acc[128 x d] += G (A, K-major) * T_j (B, MN-major), accumulator resident over the row sweep;
+//   * the dT consumer that currently owns column j reads the SAME bytes as the MN-major operand G^T:
+//       acc[128 x d] += G^T (A, MN-major) * I_i (B, MN-major).
+// Relaxed flags in global memory carry the hand-off (`ready`: tile stored; `done_i` / `done_t`: tile
+// fetched by the dI / dT consumer, ring slot reusable).  (Round-2 measurement: pushing the tile to a
+// cluster peer over DSMEM, 18 B/cycle, kept the producer's TMA engine busy for 1800 cycles per tile;
+// the L2 ring costs one 32 KB store per tile and needs no clusters.)
+// The skewed schedule of grad_sched.cuh makes the producers hit distinct columns at every step and
+// gives each column its tiles in bursts, so a dT consumer keeps ONE column accumulator resident
+// for a burst ("piece") and then adds it to the column's sum in rank order (`col_turn`): TMA
+// store for the first piece, TMA reduce-add (performed in L2, no read traffic) for the others;
+// one piece adds at a time, in fixed order, so dT is bit-reproducible.  When the final rows are
+// not plain local fp32 (bf16 output, or the NVLink peer windows of the fused reduce-scatter), the
+// pieces collect in an fp32 partial buffer and the last piece reads it back on its way out.
+//
+// Blocks [0, np): producers; [np, 2 np): dI consumers; [2 np, 2 np + nq): dT consumers.
+// All CTAs are co-resident (grid <= SM count, one CTA per SM): the flags are spin-waited.
+
+constexpr int GB_SMX_GROUPS = 4;          // column groups of the S tile: 4 softmax warps each
+constexpr int GB_SMX_COLS = 128 / GB_SMX_GROUPS;
+constexpr int GB_SMX_WARPS = 4 * GB_SMX_GROUPS;
+constexpr int GB_STORE_WARP = 2 + GB_SMX_WARPS;
+constexpr int GB_THREADS = 32 * (GB_STORE_WARP + 1);   // TMA + MMA + softmax warps + store warp
+constexpr int GB_P_STAGES = 5;            // producer ring: 5 x 32 KB (4 are one tile: no slack at the
+                                          // ~1750-cycle L2 latency, see profiles/r02_pipeline_experiments.txt)
+constexpr int GB_C_STAGES = 4;
+constexpr int GB_STAGE_BYTES = 32768;
+constexpr int GB_RING_DEPTH = 8;          // G tiles per producer in the global ring
+constexpr int GB_EPI_WARPS = 8;           // consumers: warps 2..9 flush the accumulator (two per TMEM lane quarter)
+constexpr int GB_EPI_BYTES = GB_EPI_WARPS * 4096;
+constexpr int GB_BAR_BYTES = 1024;
+constexpr int GB_SMEM_USED = GB_BAR_BYTES + G_SLOTS * G_SLOT_BYTES + GB_P_STAGES * GB_STAGE_BYTES;
+constexpr int GB_SMEM = GB_SMEM_USED + 1024;   // + alignment slack
+constexpr int GB_FLAG_STRIDE = 8;         // ints: every flag in its own 32-byte sector
+static_assert(GB_BAR_BYTES + G_SLOTS * G_SLOT_BYTES + GB_C_STAGES * GB_STAGE_BYTES + GB_EPI_BYTES <=
+                  GB_SMEM_USED, "consumer layout must fit the producer's");
+static_assert(GB_SMEM <= 232448, "shared memory per block");
+
+struct GradBothParams {
+  GradParams g;          // X = I: statistics, dI output, dI partial slots, dscale partials
+  void* dy;              // [n_cols, d] dT (fp32 or bf16), or nullptr with dy_scatter
+  int dy_bf16;
+  int dy_direct;         // final rows are local fp32: every piece goes straight to dy (TMA store / reduce-add)
+  const float* dy_mul;   // optional upstream gradient folded into the dT rows
+  RowScatter dy_scatter;
+  float* dy_part;        // indirect mode: [total_tiles * 128, d] fp32 partial sums
+  uint8_t* gring;        // [np][GB_RING_DEPTH][32 KB]
+  int* ready;            // [np]: nominal steps published by producer a (tiles < ready are in the ring)
+  int* done_i;           // [np][GB_RING_DEPTH]: step + 1 of the tile the dI consumer last fetched from the slot
+  int* done_t;           // ... the dT consumers
+  int* col_turn;         // [total_tiles]: rank of the piece that may add to the column next
+  int np;                // producer slots (= s.np)
+  Sched s;
+};
+
+struct GbBarriers {
+  uint64_t full[GB_P_STAGES];
+  uint64_t empty[GB_P_STAGES];
+  uint64_t s_full[2];
+  uint64_t s_empty[2];
+  uint64_t x_ready;
+  uint64_t x_free;
+  uint64_t g_full[G_SLOTS];     // consumers: G tile landed (bulk load)
+  uint64_t g_empty[G_SLOTS];    // consumers: G slot consumed by the MMAs
+  uint64_t g_staged[G_SLOTS];   // producer: softmax warps -> store warp
+  uint64_t g_stored[G_SLOTS];   // producer: store warp has read the slot
+  uint64_t acc_full;
+  uint64_t acc_free;
+  uint32_t tmem_base;
+  int ring_last[GB_RING_DEPTH]; // producer's store warp: step of the tile last written to each ring slot
+};
+static_assert(sizeof(GbBarriers) <= GB_BAR_BYTES, "barrier block");
+
+// A protocol bug must not hang the GPU: every wait of this kernel traps after ~2 s.
+__device__ __forceinline__ void gb_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("vlpclip grad_both: barrier wait timed out (block %d warp %d bar 0x%x)\n", blockIdx.x,
+             threadIdx.x >> 5, bar);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void gb_poll_ge(const int* flag, int target) {
+  if (ld_acquire_gpu(flag) >= target) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(flag) < target) {
+    __nanosleep(32);
+    if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("vlpclip grad_both: flag wait timed out (block %d warp %d target %d)\n", blockIdx.x,
+             threadIdx.x >> 5, target);
+      __trap();
+    }
+  }
+}
+
+// -DVLP_PROFILE_WAITS: cycles each role spends blocked (dev tool; counters per CTA, see tools/check_grad_both.py)
+#ifdef VLP_PROFILE_WAITS
+#define GBW(idx, stmt)                  \
+  do {                                  \
+    const long long t0__ = clock64();   \
+    stmt;                               \
+    gbw[idx] += clock64() - t0__;       \
+  } while (0)
+#else
+#define GBW(idx, stmt) stmt
+#endif
+
+// producer-side iteration: the waves in which slot `a` holds a virtual row
+struct ProdIter {
+  const Sched& s;
+  int a, pi, w;
+  __device__ ProdIter(const Sched& sched, int slot) : s(sched), a(slot), pi(0), w(-1) {}
+  __device__ bool next(VRow& vr, int& t_base) {
+    while (pi < s.n_ph) {
+      const SchedPhase& p = s.ph[pi];
+      ++w;
+      if (w >= p.n_waves) {
+        ++pi;
+        w = -1;
+        continue;
+      }
+      if (sched_vrow(s, p, w, a, vr)) {
+        t_base = p.t0 + w * p.cs;
+        return true;
+      }
+    }
+    return false;
+  }
+  __device__ const SchedPhase& phase() const { return s.ph[pi]; }
+};
+
+// ---- softmax of NC logits of one row (see softmax_tile / softmax_tile_fast in grad_bwd.cu) -------
+template <bool kDiag, int NC>
+__device__ __forceinline__ void gb_softmax(const uint32_t (&v)[NC], const float4* __restrict__ ymax4,
+                                           const float4* __restrict__ ylg4, float xmax, float xlg,
+                                           float scale_log2, float diag_val, int diag_j,
+                                           uint32_t (&out)[NC / 2], float& ds_acc) {
+#pragma unroll
+  for (int q = 0; q < NC / 4; ++q) {
+    const float4 ym = __ldg(ymax4 + q);
+    const float4 yl = __ldg(ylg4 + q);
+    const float ymv[4] = {ym.x, ym.y, ym.z, ym.w};
+    const float ylv[4] = {yl.x, yl.y, yl.z, yl.w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q * 4 + e;
+      const float s = __uint_as_float(v[j]);
+      const float a = ex2_approx(fmaf(s - xmax, scale_log2, -xlg));
+      const float b = ex2_approx(fmaf(s - ymv[e], scale_log2, -ylv[e]));
+      float gg = a + b;
+      if (kDiag) gg = (j == diag_j) ? diag_val : gg;
+      ds_acc = fmaf(gg, s, ds_acc);
+      g[e] = gg * G_SCALE;
+    }
+    out[q * 2 + 0] = pack_f16x2(g[0], g[1]);
+    out[q * 2 + 1] = pack_f16x2(g[2], g[3]);
+  }
+}
+template <bool kDiag, int NC>
+__device__ __forceinline__ void gb_softmax_fast(const uint32_t (&v)[NC], const float4* __restrict__ yc4,
+                                                float xmax, float xlg13, float xr, float scale_log2,
+                                                float diag_val_scaled, int diag_j,
+                                                uint32_t (&out)[NC / 2], float& ds_acc) {
+#pragma unroll
+  for (int q = 0; q < NC / 4; ++q) {
+    const float4 yc = __ldg(yc4 + q);
+    const float ycv[4] = {yc.x, yc.y, yc.z, yc.w};
+    float g[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q * 4 + e;
+      const float s = __uint_as_float(v[j]);
+      const float a = ex2_approx(fmaf(s - xmax, scale_log2, -xlg13));
+      float gg = fmaf(a, xr * ycv[e], a);
+      if (kDiag) gg = (j == diag_j) ? diag_val_scaled : gg;
+      ds_acc = fmaf(gg, s, ds_acc);
+      g[e] = gg;
+    }
+    out[q * 2 + 0] = pack_f16x2(g[0], g[1]);
+    out[q * 2 + 1] = pack_f16x2(g[2], g[3]);
+  }
+}
+
+// TMA tile store / reduce-add (fp32 add performed in L2) of a [32 rows x 32 fp32] smem tile
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t src_smem, int32_t c0,
+                                                  int32_t c1) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+      :
+      : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// Accumulator columns [c_begin, c_end) of a [128 rows x ncols] block (TMEM, one row per lane) ->
+// global rows through per-thread stores.  dst rows `orow8` (fp32, or bf16 when as_bf16), optionally
+// summed with the fp32 rows `prow8` first (kRmw); values are multiplied by mulv on the way out.  The
+// 32 x 32 chunk of a warp goes through a swizzled smem tile so that every store instruction writes
+// four full 128-byte lines (matters most for NVLink peer stores).
+template <bool kRmw>
+__device__ __forceinline__ void gb_flush(uint32_t tmem, uint32_t lane_addr, uint32_t stg, uint32_t lane,
+                                         int c_begin, int c_end, int cbase, int d,
+                                         uint8_t* const (&orow8)[8], const float* const (&prow8)[8],
+                                         const bool (&ok8)[8], bool as_bf16, float mulv) {
+  const int sub = lane >> 3, ch = lane & 7;
+  for (int cc = c_begin; cc < c_end; cc += 32) {
+    const int col = cbase + cc + ch * 4;
+    float4 prev[8];
+    if (kRmw) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        prev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok8[i] && col < d) prev[i] = ld_cg_f4(prow8[i] + col);
+      }
+    }
+    uint32_t v[32];
+    tmem_ld_x32(tmem + lane_addr + cc, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t a = stg + lane * 128 + ((c ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v[c * 4 + 0]),
+                   "r"(v[c * 4 + 1]), "r"(v[c * 4 + 2]), "r"(v[c * 4 + 3])
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + sub;
+      float4 o;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                   : "r"(stg + r * 128 + ((ch ^ (r & 7)) << 4))
+                   : "memory");
+      if (kRmw) {
+        o.x += prev[i].x;
+        o.y += prev[i].y;
+        o.z += prev[i].z;
+        o.w += prev[i].w;
+      }
+      o.x *= mulv;
+      o.y *= mulv;
+      o.z *= mulv;
+      o.w *= mulv;
+      if (ok8[i] && col < d) {
+        if (as_bf16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 w;
+          w.x = *reinterpret_cast<uint32_t*>(&lo);
+          w.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(orow8[i] + (size_t)col * 2) = w;
+        } else {
+          *reinterpret_cast<float4*>(orow8[i] + (size_t)col * 4) = o;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// The same block through TMA: each warp's 32 x 32 fp32 chunk (times mulv) is staged in its swizzled
+// smem tile and leaves as ONE tile store (kAdd = false) or reduce-add (kAdd = true: += in L2);
+// rows / columns outside the tensor are clipped by the tensor map.  Returns with every operation
+// complete (performed in global memory).
+template <bool kAdd>
+__device__ __forceinline__ void gb_flush_tma(uint32_t tmem, uint32_t lane_addr, uint32_t stg,
+                                             uint32_t lane, int c_begin, int c_end, int cbase,
+                                             const CUtensorMap* map, int row0, float mulv) {
+  for (int cc = c_begin; cc < c_end; cc += 32) {
+    uint32_t v[32];
+    tmem_ld_x32(tmem + lane_addr + cc, v);
+    tmem_ld_wait();
+    if (cc > c_begin) {   // the previous chunk must have left the staging tile
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t a = stg + lane * 128 + ((c ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a),
+                   "f"(__uint_as_float(v[c * 4 + 0]) * mulv), "f"(__uint_as_float(v[c * 4 + 1]) * mulv),
+                   "f"(__uint_as_float(v[c * 4 + 2]) * mulv), "f"(__uint_as_float(v[c * 4 + 3]) * mulv)
+                   : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (kAdd)
+        tma_reduce_add_2d(map, stg, cbase + cc, row0);
+      else
+        tma_store_2d(map, stg, cbase + cc, row0);
+      tma_store_commit();
+    }
+  }
+  if (lane == 0) tma_store_wait<0>();
+  __syncwarp();
+}
+
+// consumer TMA warp: fetch the G tile (slot a, step t) from the ring into local slot `slot`
+__device__ __forceinline__ void gb_fetch_g(const GradBothParams& P, GbBarriers* bars, uint32_t gslots,
+                                           uint32_t lane, int a, int t, uint32_t slot) {
+  if (lane == 0) gb_poll_ge(P.ready + (size_t)a * GB_FLAG_STRIDE, t + 1);
+  __syncwarp();
+  // (no proxy fence here: issued by a warp with TMA loads in flight it waits for all of them,
+  //  ~1500 cycles per tile; the tile's bytes were reported written to L2 before the flag was set)
+  if (elect_one()) {
+    mbar_expect_tx(smem_u32(&bars->g_full[slot]), G_SLOT_BYTES);
+    bulk_load_1d(gslots + slot * G_SLOT_BYTES,
+                 P.gring + (((size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH)) << 15), G_SLOT_BYTES,
+                 smem_u32(&bars->g_full[slot]));
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(GB_THREADS, 1)
+grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k, 128 rows}
+                 const __grid_constant__ CUtensorMap map_y_mn,  // T: box {64 d, 64 rows}
+                 const __grid_constant__ CUtensorMap map_x_mn,  // I: box {64 d, 64 rows}
+                 const __grid_constant__ CUtensorMap map_dy,    // dT sum (dy or dy_part) fp32: box {32, 32}
+                 const __grid_constant__ GradBothParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  GbBarriers* bars = reinterpret_cast<GbBarriers*>(smem);
+  const uint32_t gslots = smem_u32(smem) + GB_BAR_BYTES;
+  const uint32_t ring = gslots + G_SLOTS * G_SLOT_BYTES;
+  const uint32_t stage = ring + GB_C_STAGES * GB_STAGE_BYTES;   // consumers: epilogue staging
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const int bid = blockIdx.x;
+  const GradParams& p = P.g;
+  const Sched& S = P.s;
+#ifdef VLP_PROFILE_WAITS
+  long long gbw[16] = {0};
+  const long long kernel_t0 = clock64();
+#endif
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GB_P_STAGES; ++i) {
+      mbar_init(smem_u32(&bars->full[i]), 1);
+      mbar_init(smem_u32(&bars->empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->s_full[i]), 1);
+      mbar_init(smem_u32(&bars->s_empty[i]), GB_SMX_WARPS);
+      mbar_init(smem_u32(&bars->g_full[i]), 1);
+      mbar_init(smem_u32(&bars->g_empty[i]), 1);
+      mbar_init(smem_u32(&bars->g_staged[i]), GB_SMX_WARPS);
+      mbar_init(smem_u32(&bars->g_stored[i]), 1);
+    }
+    mbar_init(smem_u32(&bars->x_ready), 8);
+    mbar_init(smem_u32(&bars->x_free), 1);
+    mbar_init(smem_u32(&bars->acc_full), 1);
+    mbar_init(smem_u32(&bars->acc_free), GB_EPI_WARPS);
+    for (int i = 0; i < GB_RING_DEPTH; ++i) bars->ring_last[i] = -1;
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(smem_u32(&bars->tmem_base), 512);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_y_k);
+    tma_prefetch_desc(&map_y_mn);
+    tma_prefetch_desc(&map_x_mn);
+    tma_prefetch_desc(&map_dy);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const float scale_dev = __ldg(p.scale_ptr);
+  const float scale_log2 = scale_dev * kLog2e;
+  const uint32_t nbuf = p.kblocks <= 8 ? 2u : 1u;
+  const uint32_t tmem_s_col = 512u - nbuf * 128u;
+  const int n_nc = (p.ndb + 3) / 4;   // 256-wide accumulator chunks of this pass
+
+  if (bid < P.np) {
+    // =====================================================================================
+    // producer slot a: S tiles + softmax -> G tiles, stored to the ring
+    // =====================================================================================
+    const int a = bid;
+    if (warp == 0) {
+      uint32_t it = 0;
+      ProdIter items(S, a);
+      VRow vr;
+      int t_base;
+      while (items.next(vr, t_base)) {
+        const SchedPhase& ph = items.phase();
+        for (int u = 0; u < ph.cs; ++u) {
+          const int col = sched_col(ph, vr, a, u);
+          if (col < 0) continue;
+          for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
+            const uint32_t st = it % GB_P_STAGES, par = (it / GB_P_STAGES) & 1;
+            const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
+            GBW(0, gb_wait(smem_u32(&bars->empty[st]), par ^ 1));
+            if (elect_one()) {
+              mbar_expect_tx(smem_u32(&bars->full[st]), nkb * P_BOX_BYTES);
+              for (int q = 0; q < nkb; ++q)
+                tma_load_2d(ring + st * GB_STAGE_BYTES + q * P_BOX_BYTES, &map_y_k,
+                            smem_u32(&bars->full[st]), (kb + q) * 64, col * 128);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_K, 128, 128);
+      uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+      ProdIter items(S, a);
+      VRow vr;
+      int t_base;
+      for (; items.next(vr, t_base); ++item_ctr) {
+        const SchedPhase& ph = items.phase();
+        GBW(1, gb_wait(smem_u32(&bars->x_ready), item_ctr & 1));
+        tc_fence_after();
+        for (int u = 0; u < ph.cs; ++u) {
+          if (sched_col(ph, vr, a, u) < 0) continue;
+          const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+          const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+          GBW(2, gb_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
+          for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
+            const uint32_t st = it % GB_P_STAGES, par = (it / GB_P_STAGES) & 1;
+            const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
+            GBW(3, gb_wait(smem_u32(&bars->full[st]), par));
+            tc_fence_after();
+            if (elect_one()) {
+              for (int q = 0; q < nkb; ++q) {
+                const uint32_t sb = ring + st * GB_STAGE_BYTES + q * P_BOX_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_ts<1>(d_tmem, tmem + BWD_TMEM_X + (kb + q) * 32 + ks * 8,
+                             make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | q | ks) != 0);
+              }
+              umma_commit<1>(smem_u32(&bars->empty[st]));
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit<1>(smem_u32(&bars->s_full[buf]));
+          __syncwarp();
+          ++tile_ctr;
+        }
+        if (elect_one()) umma_commit<1>(smem_u32(&bars->x_free));
+        __syncwarp();
+      }
+      if (item_ctr > 0) gb_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+    } else if (warp < GB_STORE_WARP) {
+      // ---- softmax warps: thread = (row, 32-column group) ----
+      const uint32_t quarter = warp & 3;
+      const uint32_t grp = (warp - 2) >> 2;
+      const uint32_t row_in_blk = quarter * 32 + lane;
+      const uint32_t lane_addr = (quarter * 32u) << 16;
+      const int dp = p.kblocks * 64;
+      const uint32_t sw = row_in_blk & 7;
+      uint32_t tile_ctr = 0, item_ctr = 0;
+      double ds_total = 0.0;
+      const bool fast = *p.fast_flag != 0;
+      ProdIter items(S, a);
+      VRow vr;
+      int t_base;
+      for (; items.next(vr, t_base); ++item_ctr) {
+        const SchedPhase& ph = items.phase();
+        const int row = vr.rb * 128 + row_in_blk;
+        const bool row_ok = row < p.n_rows;
+        if (item_ctr > 0) {
+          gb_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+          tc_fence_after();
+        }
+        if (grp < 2) {   // 8 warps stage the X block (two K halves) into TMEM
+          const int k_begin = grp * (dp / 2);
+          const uint4* src =
+              reinterpret_cast<const uint4*>(p.x + (size_t)(row_ok ? row : 0) * p.ldx);
+          for (int c0 = 0; c0 < dp / 4; c0 += 16) {
+            uint32_t xv[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int k = k_begin + c0 * 2 + q * 8;
+              uint4 w = make_uint4(0, 0, 0, 0);
+              if (row_ok && k < p.d) w = __ldg(src + (k >> 3));
+              xv[q * 4 + 0] = w.x;
+              xv[q * 4 + 1] = w.y;
+              xv[q * 4 + 2] = w.z;
+              xv[q * 4 + 3] = w.w;
+            }
+            tmem_st_x16(tmem + lane_addr + BWD_TMEM_X + k_begin / 2 + c0, xv);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
+        }
+        const float xmax = p.xmax[row];
+        const float xlg = p.xlg[row];
+        const float xr = p.xr[row];
+        const int dcol = row_ok ? row - p.diag_shift : -1000000000;
+        float ds_acc = 0.f;
+
+        for (int u = 0; u < ph.cs; ++u) {
+          const int col = sched_col(ph, vr, a, u);
+          if (col < 0) continue;
+          const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+          const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+          GBW(4, gb_wait(smem_u32(&bars->s_full[buf]), use & 1));
+          tc_fence_after();
+          uint32_t v[GB_SMX_COLS];
+          tmem_ld_x32(tmem + lane_addr + tmem_s_col + buf * 128 + grp * GB_SMX_COLS, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
+
+          const int col0 = col * 128 + grp * GB_SMX_COLS;
+          uint32_t out[GB_SMX_COLS / 2];
+          const int diag_j = dcol - col0;
+          const bool has_diag = diag_j >= 0 && diag_j < GB_SMX_COLS;
+          const bool any_diag = __any_sync(0xffffffffu, has_diag);
+          float diag_val = 0.f;
+          if (has_diag) diag_val = -(p.w_row * p.xq[row] + p.w_col * p.yq[dcol]);
+          if (fast) {
+            const float4* yc4 = reinterpret_cast<const float4*>(p.yc + col0);
+            float acc = 0.f;
+            if (any_diag)
+              gb_softmax_fast<true, GB_SMX_COLS>(v, yc4, xmax, xlg - 13.f, xr, scale_log2,
+                                                 diag_val * G_SCALE, diag_j, out, acc);
+            else
+              gb_softmax_fast<false, GB_SMX_COLS>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, 0.f, diag_j,
+                                                  out, acc);
+            ds_acc = fmaf(acc, 1.0f / G_SCALE, ds_acc);
+          } else {
+            const float4* ymax4 = reinterpret_cast<const float4*>(p.ymax + col0);
+            const float4* ylg4 = reinterpret_cast<const float4*>(p.ylg + col0);
+            if (any_diag)
+              gb_softmax<true, GB_SMX_COLS>(v, ymax4, ylg4, xmax, xlg, scale_log2, diag_val, diag_j, out,
+                                            ds_acc);
+            else
+              gb_softmax<false, GB_SMX_COLS>(v, ymax4, ylg4, xmax, xlg, scale_log2, 0.f, diag_j, out,
+                                             ds_acc);
+          }
+
+          // stage the fp16 G tile (K-major, 128B swizzle): the store warp must have read the slot's
+          // previous tile
+          const uint32_t slot = tile_ctr & 1;
+          if (tile_ctr >= 2) GBW(6, gb_wait(smem_u32(&bars->g_stored[slot]), ((tile_ctr >> 1) - 1) & 1));
+          const uint32_t dst = gslots + slot * G_SLOT_BYTES + ((grp * GB_SMX_COLS) >> 6) * 16384 +
+                               row_in_blk * 128;
+          const uint32_t cb = ((grp * GB_SMX_COLS) & 63) >> 3;
+#pragma unroll
+          for (int c = 0; c < GB_SMX_COLS / 8; ++c) {
+            const uint32_t sa = dst + (((cb + c) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa), "r"(out[c * 4 + 0]),
+                         "r"(out[c * 4 + 1]), "r"(out[c * 4 + 2]), "r"(out[c * 4 + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->g_staged[slot]));
+          ++tile_ctr;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ds_acc += __shfl_xor_sync(0xffffffffu, ds_acc, o);
+        ds_total += (double)ds_acc;
+      }
+      if (p.ds_part != nullptr && lane == 0)
+        p.ds_part[(size_t)a * GB_SMX_WARPS + (warp - 2)] = (float)ds_total;
+      // drain: the store warp must have read every slot we staged before we may exit
+      for (uint32_t back = 0; back < 2 && back < tile_ctr; ++back) {
+        const uint32_t tc = tile_ctr - 1 - back;
+        gb_wait(smem_u32(&bars->g_stored[tc & 1]), (tc >> 1) & 1);
+      }
+    } else {
+      // ---- store warp: staged G tiles -> global ring, published with a flag ----
+      // The flag is a relaxed store issued after cp.async.bulk.wait_group has reported the tile's
+      // bytes written (a release fence here costs ~1500 cycles per tile); readers acquire-load the
+      // flag and fence the async proxy before their bulk load.
+      uint32_t tile_ctr = 0;
+      int pf_rs = -1, pf_i = 0, pf_t = 0;
+      int* ready = P.ready + (size_t)a * GB_FLAG_STRIDE;
+      const int* done_i = P.done_i + (size_t)a * GB_RING_DEPTH * GB_FLAG_STRIDE;
+      const int* done_t = P.done_t + (size_t)a * GB_RING_DEPTH * GB_FLAG_STRIDE;
+      ProdIter items(S, a);
+      VRow vr;
+      int t_base;
+      while (items.next(vr, t_base)) {
+        const SchedPhase& ph = items.phase();
+        for (int u = 0; u < ph.cs; ++u) {
+          if (sched_col(ph, vr, a, u) < 0) continue;
+          const int t = t_base + u;
+          const uint32_t slot = tile_ctr & 1;
+          GBW(8, gb_wait(smem_u32(&bars->g_staged[slot]), (tile_ctr >> 1) & 1));
+          if (lane == 0) {
+            const int rs = t % GB_RING_DEPTH;
+            const int last = bars->ring_last[rs];
+            if (last >= 0) {   // both readers of the slot's previous tile must have fetched it
+              if (!(pf_rs == rs && pf_i >= last + 1)) GBW(9, gb_poll_ge(done_i + rs * GB_FLAG_STRIDE, last + 1));
+              if (!(pf_rs == rs && pf_t >= last + 1)) GBW(9, gb_poll_ge(done_t + rs * GB_FLAG_STRIDE, last + 1));
+            }
+            bars->ring_last[rs] = t;
+            bulk_store_1d(P.gring + (((size_t)a * GB_RING_DEPTH + rs) << 15),
+                          gslots + slot * G_SLOT_BYTES, G_SLOT_BYTES);
+            tma_store_commit();
+            pf_rs = (rs + 1) % GB_RING_DEPTH;        // flags of the slot the next tile will use
+            pf_i = ld_acquire_gpu(done_i + pf_rs * GB_FLAG_STRIDE);
+            pf_t = ld_acquire_gpu(done_t + pf_rs * GB_FLAG_STRIDE);
+            GBW(10, tma_store_wait_read<0>());              // the slot may be restaged
+            mbar_arrive(smem_u32(&bars->g_stored[slot]));
+            GBW(11, tma_store_wait<0>());                   // the tile is in global memory: publish
+            GBW(12, st_relaxed_gpu(ready, t + 1));
+          }
+          __syncwarp();
+          ++tile_ctr;
+        }
+      }
+    }
+  } else if (bid < 2 * P.np) {
+    // =====================================================================================
+    // dI consumer of producer slot a: row-resident accumulator
+    // =====================================================================================
+    const int a = bid - P.np;
+    if (warp == 0) {
+      uint32_t it = 0, tile_ctr = 0;
+      ProdIter items(S, a);
+      VRow vr;
+      int t_base;
+      while (items.next(vr, t_base)) {
+        const SchedPhase& ph = items.phase();
+        for (int u = 0; u < ph.cs; ++u) {
+          const int col = sched_col(ph, vr, a, u);
+          if (col < 0) continue;
+          const uint32_t slot = tile_ctr & 1;
+          if (tile_ctr >= 2) GBW(0, gb_wait(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
+          GBW(1, gb_fetch_g(P, bars, gslots, lane, a, t_base + u, slot));
+          for (int nc = 0; nc < n_nc; ++nc) {
+            const int nb = min(4, p.ndb - nc * 4);
+            for (int kh = 0; kh < 2; ++kh, ++it) {
+              const uint32_t st = it % GB_C_STAGES, par = (it / GB_C_STAGES) & 1;
+              GBW(2, gb_wait(smem_u32(&bars->empty[st]), par ^ 1));
+              if (elect_one()) {
+                mbar_expect_tx(smem_u32(&bars->full[st]), nb * 8192);
+                for (int b = 0; b < nb; ++b)
+                  tma_load_2d(ring + st * GB_STAGE_BYTES + b * 8192, &map_y_mn,
+                              smem_u32(&bars->full[st]), (p.db0 + nc * 4 + b) * 64,
+                              col * 128 + kh * 64);
+              }
+              __syncwarp();
+            }
+          }
+          ++tile_ctr;
+        }
+      }
+    } else if (warp == 1) {
+      uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+      ProdIter items(S, a);
+      VRow vr;
+      int t_base;
+      for (; items.next(vr, t_base); ++item_ctr) {
+        const SchedPhase& ph = items.phase();
+        if (item_ctr > 0) {
+          GBW(3, gb_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1));
+          tc_fence_after();
+        }
+        bool first = true;
+        for (int u = 0; u < ph.cs; ++u) {
+          if (sched_col(ph, vr, a, u) < 0) continue;
+          const int t = t_base + u;
+          const uint32_t slot = tile_ctr & 1;
+          GBW(4, gb_wait(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
+          tc_fence_after();
+          if (lane == 0)   // the tile sits in shared memory: this reader is done with the ring slot
+            st_relaxed_gpu(P.done_i + ((size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH)) * GB_FLAG_STRIDE, t + 1);
+          const uint32_t ga = gslots + slot * G_SLOT_BYTES;
+          for (int nc = 0; nc < n_nc; ++nc) {
+            const int nb = min(4, p.ndb - nc * 4);
+            const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
+            for (int kh = 0; kh < 2; ++kh, ++it) {
+              const uint32_t st = it % GB_C_STAGES, par = (it / GB_C_STAGES) & 1;
+              GBW(5, gb_wait(smem_u32(&bars->full[st]), par));
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t sb = ring + st * GB_STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint64_t ad = make_sdesc_sw128(ga + kh * 16384 + i * 32, 0, 1024);
+                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, 8192, 1024);
+                  umma_ss<1>(tmem + nc * 256, ad, bd, idesc, !(first && kh == 0 && i == 0));
+                }
+                umma_commit<1>(smem_u32(&bars->empty[st]));
+              }
+              __syncwarp();
+            }
+          }
+          if (elect_one()) umma_commit<1>(smem_u32(&bars->g_empty[slot]));
+          __syncwarp();
+          first = false;
+          ++tile_ctr;
+        }
+        if (elect_one()) umma_commit<1>(smem_u32(&bars->acc_full));
+        __syncwarp();
+      }
+    } else if (warp < 2 + GB_EPI_WARPS) {
+      const uint32_t quarter = warp & 3;
+      const uint32_t lane_addr = (quarter * 32u) << 16;
+      const int half = (warp - 2) >> 2;                       // column half of the accumulator
+      const int c_half = ((p.ndb * 64 / 2) + 31) & ~31;
+      const int c_begin = half * c_half, c_end = half ? p.ndb * 64 : c_half;
+      uint32_t item_ctr = 0;
+      ProdIter items(S, a);
+      VRow vr;
+      int t_base;
+      for (; items.next(vr, t_base); ++item_ctr) {
+        GBW(6, gb_wait(smem_u32(&bars->acc_full), item_ctr & 1));
+        tc_fence_after();
+        const bool final_out = vr.part < 0;
+        const float mulv =
+            scale_dev * ((final_out && p.out_mul) ? p.out_scale * __ldg(p.out_mul) : p.out_scale);
+        const int sub = lane >> 3;
+        uint8_t* orow8[8];
+        const float* prow8[8];
+        bool ok8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + sub;
+          const int grow = vr.rb * 128 + (int)quarter * 32 + r;
+          ok8[i] = grow < p.n_rows;
+          prow8[i] = nullptr;
+          if (final_out) {
+            uint8_t* base;
+            const size_t rr = scatter_row(p.scatter, ok8[i] ? grow : 0, base, p.dx);
+            orow8[i] = base + rr * p.d * (p.dx_bf16 ? 2 : 4);
+          } else {
+            orow8[i] = reinterpret_cast<uint8_t*>(
+                p.part + ((size_t)vr.part * 128 + quarter * 32 + r) * p.d);
+          }
+        }
+        GBW(7, gb_flush<false>(tmem, lane_addr, stage + (warp - 2) * 4096, lane, c_begin, c_end, p.db0 * 64,
+                               p.d, orow8, prow8, ok8, final_out && p.dx_bf16, mulv));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_free));
+      }
+    }
+  } else if (bid < 2 * P.np + S.nq) {
+    // =====================================================================================
+    // dT consumer q: column-resident accumulator
+    // =====================================================================================
+    const int q = bid - 2 * P.np;
+    if (warp == 0) {
+      uint32_t it = 0, tile_ctr = 0;
+      PieceIter pieces(S, q);
+      Piece pc;
+      while (pieces.next(pc)) {
+        for (int a = pc.a_hi; a >= pc.a_lo; --a, ++tile_ctr) {
+          const int t = pc.t_hi + (pc.a_hi - a), rb = pc.rb_hi - (pc.a_hi - a);
+          const uint32_t slot = tile_ctr & 1;
+          if (tile_ctr >= 2) GBW(0, gb_wait(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
+          GBW(1, gb_fetch_g(P, bars, gslots, lane, a, t, slot));
+          for (int nc = 0; nc < n_nc; ++nc) {
+            const int nb = min(4, p.ndb - nc * 4);
+            for (int kh = 0; kh < 2; ++kh, ++it) {
+              const uint32_t st = it % GB_C_STAGES, par = (it / GB_C_STAGES) & 1;
+              GBW(2, gb_wait(smem_u32(&bars->empty[st]), par ^ 1));
+              if (elect_one()) {
+                mbar_expect_tx(smem_u32(&bars->full[st]), nb * 8192);
+                for (int b = 0; b < nb; ++b)
+                  tma_load_2d(ring + st * GB_STAGE_BYTES + b * 8192, &map_x_mn,
+                              smem_u32(&bars->full[st]), (p.db0 + nc * 4 + b) * 64,
+                              rb * 128 + kh * 64);
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      uint32_t it = 0, tile_ctr = 0, piece_ctr = 0;
+      PieceIter pieces(S, q);
+      Piece pc;
+      for (; pieces.next(pc); ++piece_ctr) {
+        if (piece_ctr > 0) {
+          GBW(3, gb_wait(smem_u32(&bars->acc_free), (piece_ctr - 1) & 1));
+          tc_fence_after();
+        }
+        for (int a = pc.a_hi; a >= pc.a_lo; --a, ++tile_ctr) {
+          const int t = pc.t_hi + (pc.a_hi - a);
+          const uint32_t slot = tile_ctr & 1;
+          GBW(4, gb_wait(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
+          tc_fence_after();
+          if (lane == 0)
+            st_relaxed_gpu(P.done_t + ((size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH)) * GB_FLAG_STRIDE, t + 1);
+          const uint32_t ga = gslots + slot * G_SLOT_BYTES;
+          for (int nc = 0; nc < n_nc; ++nc) {
+            const int nb = min(4, p.ndb - nc * 4);
+            // A = G^T: the K-major tile the producer staged, read MN-major (M = column j, K = row i)
+            const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_MN, MAJOR_MN, 128, nb * 64);
+            for (int kh = 0; kh < 2; ++kh, ++it) {
+              const uint32_t st = it % GB_C_STAGES, par = (it / GB_C_STAGES) & 1;
+              GBW(5, gb_wait(smem_u32(&bars->full[st]), par));
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t sb = ring + st * GB_STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint64_t ad = make_sdesc_sw128(ga + (kh * 4 + i) * 2048, 16384, 1024);
+                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, 8192, 1024);
+                  umma_ss<1>(tmem + nc * 256, ad, bd, idesc, !(a == pc.a_hi && kh == 0 && i == 0));
+                }
+                umma_commit<1>(smem_u32(&bars->empty[st]));
+              }
+              __syncwarp();
+            }
+          }
+          if (elect_one()) umma_commit<1>(smem_u32(&bars->g_empty[slot]));
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit<1>(smem_u32(&bars->acc_full));
+        __syncwarp();
+      }
+    } else if (warp < 2 + GB_EPI_WARPS) {
+      const uint32_t quarter = warp & 3;
+      const uint32_t lane_addr = (quarter * 32u) << 16;
+      const int half = (warp - 2) >> 2;
+      const int c_half = ((p.ndb * 64 / 2) + 31) & ~31;
+      const int c_begin = half * c_half, c_end = half ? p.ndb * 64 : c_half;
+      const uint32_t stg = stage + (warp - 2) * 4096;
+      uint32_t piece_ctr = 0;
+      PieceIter pieces(S, q);
+      Piece pc;
+      for (; pieces.next(pc); ++piece_ctr) {
+        int prank, ptotal;
+        sched_piece_rank(S, pc.col, pc.gw, pc.wrapped, prank, ptotal);
+        GBW(6, gb_wait(smem_u32(&bars->acc_full), piece_ctr & 1));
+        tc_fence_after();
+        int* turn = P.col_turn + (size_t)pc.col * GB_FLAG_STRIDE;
+        if (prank > 0) {   // the column's earlier pieces must have been added
+          if (lane == 0) GBW(7, gb_poll_ge(turn, prank));
+          __syncwarp();
+        }
+        const bool last = prank == ptotal - 1;
+        const float mul_final = scale_dev * p.out_scale * (P.dy_mul ? __ldg(P.dy_mul) : 1.f);
+        const int row0 = pc.col * 128 + (int)quarter * 32;
+        if (P.dy_direct || !last) {
+          // direct: every piece lands in dy (scaled); indirect: the pieces before the last collect
+          // unscaled in dy_part.  First piece = tile store, later ones = reduce-add in L2.
+          const float mulv = P.dy_direct ? mul_final : 1.f;
+          if (prank > 0)
+            GBW(8, gb_flush_tma<true>(tmem, lane_addr, stg, lane, c_begin, c_end, p.db0 * 64, &map_dy, row0, mulv));
+          else
+            GBW(9, gb_flush_tma<false>(tmem, lane_addr, stg, lane, c_begin, c_end, p.db0 * 64, &map_dy, row0, mulv));
+        } else {
+          // indirect, last piece: (partial sum + accumulator) * mul -> final rows (bf16 / peer window)
+          const int sub = lane >> 3;
+          uint8_t* orow8[8];
+          const float* prow8[8];
+          bool ok8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + sub;
+            const int grow = row0 + r;
+            ok8[i] = grow < p.n_cols;
+            prow8[i] = P.dy_part + (size_t)(ok8[i] ? grow : 0) * p.d;
+            uint8_t* base;
+            const size_t rr = scatter_row(P.dy_scatter, ok8[i] ? grow : 0, base, P.dy);
+            orow8[i] = base + rr * p.d * (P.dy_bf16 ? 2 : 4);
+          }
+          if (prank > 0)
+            GBW(10, gb_flush<true>(tmem, lane_addr, stg, lane, c_begin, c_end, p.db0 * 64, p.d, orow8, prow8,
+                                   ok8, P.dy_bf16 != 0, mul_final));
+          else
+            GBW(10, gb_flush<false>(tmem, lane_addr, stg, lane, c_begin, c_end, p.db0 * 64, p.d, orow8, prow8,
+                                    ok8, P.dy_bf16 != 0, mul_final));
+        }
+        tc_fence_before();
+        if (!last) {   // hand the column to its next piece
+          __threadfence();
+          bar_sync(3, 32 * GB_EPI_WARPS);
+          if (warp == 2 && lane == 0) st_release_gpu(turn, prank + 1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_free));
+      }
+    }
+  }
+
+#ifdef VLP_PROFILE_WAITS
+  if (p.wait_prof != nullptr && lane == 0 && (warp <= 2 || warp == GB_STORE_WARP)) {
+    long long* o = p.wait_prof + (size_t)blockIdx.x * 16;
+    for (int i = 0; i < 15; ++i)
+      if (gbw[i] != 0) o[i] = gbw[i];
+    if (warp == 0) o[15] = clock64() - kernel_t0;
+  }
+#endif
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem, 512);
+}
+
+// dI rows of row blocks whose column range was split in segments (phase with n_seg > 1):
+// dx rows = mul * (segment partials summed in segment order)
+__global__ void dx_seg_reduce_kernel(const float* __restrict__ part, const SchedPhase ph, int n_rows,
+                                     int d, const float* __restrict__ out_mul, int out_bf16,
+                                     void* __restrict__ dx, const RowScatter scatter) {
+  const int rl = blockIdx.x;                 // row block within the phase
+  const int rb = ph.row0 + rl;
+  const int rows = min(128, n_rows - rb * 128);
+  const int d4 = d >> 2;
+  const float m = out_mul ? __ldg(out_mul) : 1.f;
+  const size_t blk4 = (size_t)128 * d4;
+  const float4* part4 = reinterpret_cast<const float4*>(part);
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < rows * d4; i += gridDim.y * blockDim.x) {
+    const int r = i / d4, c4 = i - r * d4;
+    const size_t off = (size_t)r * d4 + c4;
+    float4 acc = part4[(size_t)(ph.part0 + rl) * blk4 + off];
+    for (int sg = 1; sg < ph.n_seg; ++sg) {
+      const float4 b = part4[(size_t)(ph.part0 + sg * ph.n_rows + rl) * blk4 + off];
+      acc.x += b.x;
+      acc.y += b.y;
+      acc.z += b.z;
+      acc.w += b.w;
+    }
+    uint8_t* base;
+    const size_t orow = scatter_row(scatter, rb * 128 + r, base, dx);
+    if (out_bf16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x * m, acc.y * m);
+      __nv_bfloat162 hi = __floats2bfloat162_rn(acc.z * m, acc.w * m);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&lo);
+      o.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(base)[orow * d4 + c4] = o;
+    } else {
+      reinterpret_cast<float4*>(base)[orow * d4 + c4] =
+          make_float4(acc.x * m, acc.y * m, acc.z * m, acc.w * m);
+    }
+  }
+}

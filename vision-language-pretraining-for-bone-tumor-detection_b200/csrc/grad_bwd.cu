@@ -24,7 +24,9 @@
 // Neither S nor G ever leaves the SM pair.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "common.cuh"
+#include "grad_sched.cuh"
 #include "../../include/vlpclip.h"
 
 namespace vlp {
@@ -815,6 +817,8 @@ __global__ void ds_reduce_kernel(const float* __restrict__ part, int n, float mu
   if (threadIdx.x == 0) out[0] = (float)(sh[0] * (double)mul);
 }
 
+#include "grad_both.cuh"
+
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 static int n_pairs_of_device() {
@@ -851,6 +855,47 @@ static size_t grad_ws_bytes(int n_rows, int n_cols, int d) {
   const size_t partials = align256(max_pairs * 2 * 128 * (size_t)d * 4);
   return 3 * align256(nrb * 128 * 4) + 3 * align256(nt * 128 * 4) + align256(max_pairs * SMX_WARPS * 4) +
          partials + 1024;
+}
+
+
+// ---- single-recompute backward: roles and workspace layout -----------------------------------
+// n_sms SMs -> np producers, np dI consumers and nq = n_sms - 2 np >= np dT consumers (one column per
+// dT consumer at a time).  VLP_B200_GB_NP overrides the split (fewer producers = more dT consumers).
+static bool gb_roles(int n_sms, int* np_out, int* nq_out) {
+  if (n_sms < 3) return false;
+  int np = n_sms / 3;
+  const char* e = getenv("VLP_B200_GB_NP");
+  if (e && atoi(e) > 0 && atoi(e) < np) np = atoi(e);
+  *np_out = np;
+  *nq_out = n_sms - 2 * np;
+  return true;
+}
+
+struct GbLayout {
+  Sched s;
+  int n_sms, np, nq;
+  size_t off_ds, off_parts, off_dy_part, off_ring, off_flags, flag_bytes, total;
+};
+static bool gb_layout(int n_rows, int n_cols, int d, GbLayout& L) {
+  const int nrb = (n_rows + 127) / 128, nt = (n_cols + 127) / 128;
+  L.n_sms = usable_sms();
+  if (L.n_sms <= 0) L.n_sms = 148;   // no device (host-side size queries): assume a B200
+  if (!gb_roles(L.n_sms, &L.np, &L.nq)) return false;
+  L.s = make_sched(nrb, nt, L.np, L.nq);
+  size_t o = 3 * align256((size_t)nrb * 128 * 4) + 3 * align256((size_t)nt * 128 * 4) + 512;
+  L.off_ds = o;
+  o += align256((size_t)L.np * GB_SMX_WARPS * 4);
+  L.off_parts = o;
+  o += align256((size_t)L.s.n_parts * 128 * (size_t)d * 4);
+  L.off_dy_part = o;
+  o += align256((size_t)nt * 128 * (size_t)d * 4);
+  L.off_ring = o;
+  o += (size_t)L.np * GB_RING_DEPTH * G_SLOT_BYTES;
+  L.off_flags = o;
+  L.flag_bytes = ((size_t)L.np + 2 * (size_t)L.np * GB_RING_DEPTH + (size_t)nt) * GB_FLAG_STRIDE * 4;
+  o += align256(L.flag_bytes);
+  L.total = o + 1024;
+  return true;
 }
 
 }  // namespace vlp
@@ -965,12 +1010,7 @@ static int grad_impl(const void* x, int ldx, const void* y, int ldy, const float
 
   static_assert(sizeof(BwdBarriers) <= BAR_BYTES, "barrier block");
   const size_t smem = RING_BYTES + G_SLOTS * G_SLOT_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLP_CUDA_OK(cudaFuncSetAttribute(grad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    attr_set = true;
-  }
+  VLP_CUDA_OK(set_smem_attr_once((const void*)grad_pair_kernel, (int)smem, 0));
   // the dX block of a pass must fit the consumer's 512 TMEM columns: d <= 512 in one pass,
   // 512 < d <= 768 in two passes of half the 64-column blocks each (S is recomputed per pass)
   const int n_pass = p.kblocks > 8 ? 2 : 1;
@@ -1098,6 +1138,236 @@ int vlpclip_grad_scatter(const void* x, int ldx, const void* y, int ldy, const f
   return grad_impl(x, ldx, y, ldy, x_max, x_lg2l, x_q, y_max, y_lg2l, y_q, n_rows, n_cols, d, scale,
                    diag_shift, n_global, w_row, w_col, nullptr, 0, nullptr, dscale, workspace,
                    workspace_bytes, stream, &sc);
+}
+
+
+// ---- single-recompute backward: dI, dT and dscale from ONE sweep over the logit tiles ----------
+size_t vlpclip_grad_both_workspace_bytes(int n_rows, int n_cols, int d) {
+  if (n_rows <= 0 || n_cols <= 0 || d <= 0) return 0;
+  GbLayout L;
+  if (!gb_layout(n_rows, n_cols, d, L)) return 0;
+  return L.total;
+}
+
+int vlpclip_grad_both(const void* x, int ldx, const void* y, int ldy, const float* x_max,
+                      const float* x_lg2l, const float* x_q, const float* y_max,
+                      const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
+                      const float* scale, int diag_shift, int n_global, float w_row, float w_col,
+                      const float* out_mul, int dx_bf16, void* dx, int dy_bf16, void* dy,
+                      void* const* dy_owner_rows, int n_owners, int rows_per_owner, float* dscale,
+                      void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_rows <= 0 || n_cols <= 0) return fail(-1, "grad_both: empty problem (%d x %d)", n_rows, n_cols);
+  if (!x || !y || !scale || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q || !dx ||
+      (!dy && !dy_owner_rows) || !workspace)
+    return fail(-1, "grad_both: null pointer");
+  if (d <= 0 || d % 8 != 0 || d > 768)
+    return fail(-1, "grad_both: embedding dim %d unsupported (need a multiple of 8, <= 768)", d);
+  if (ldx % 8 != 0 || ldy % 8 != 0) return fail(-1, "grad_both: row strides must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(dx) & 15) != 0 || (reinterpret_cast<uintptr_t>(dy) & 15) != 0)
+    return fail(-1, "grad_both: X, Y, dX and dY must be 16-byte aligned");
+  if (n_global <= 0) return fail(-1, "grad_both: bad n_global");
+  if (!(w_row >= 0.f) || !(w_col >= 0.f) || !(w_row + w_col > 0.f))
+    return fail(-1, "grad_both: direction weights must be >= 0 and not both zero");
+  RowScatter dy_sc = {};
+  if (dy_owner_rows) {
+    if (n_owners <= 0 || n_owners > MAX_OWNERS)
+      return fail(-1, "grad_both: need 1..%d owner buffers (got %d)", MAX_OWNERS, n_owners);
+    if (rows_per_owner <= 0 || (long long)rows_per_owner * n_owners < n_cols)
+      return fail(-1, "grad_both: %d owners x %d rows do not cover %d rows", n_owners,
+                  rows_per_owner, n_cols);
+    for (int i = 0; i < n_owners; ++i) {
+      if (!dy_owner_rows[i] || (reinterpret_cast<uintptr_t>(dy_owner_rows[i]) & 15) != 0)
+        return fail(-1, "grad_both: owner buffer %d is null or not 16-byte aligned", i);
+      dy_sc.base[i] = dy_owner_rows[i];
+    }
+    dy_sc.rows_per_owner = rows_per_owner;
+  }
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  GbLayout L;
+  if (!gb_layout(n_rows, n_cols, d, L)) return fail(-1, "grad_both: needs at least 3 SMs");
+  if (workspace_bytes < L.total)
+    return fail(-1, "grad_both: workspace too small (%zu < %zu)", workspace_bytes, L.total);
+
+  GradBothParams P = {};
+  GradParams& p = P.g;
+  p.x = (const __half*)x;
+  p.ldx = ldx;
+  p.n_rows = n_rows;
+  p.n_cols = n_cols;
+  p.d = d;
+  p.kblocks = (d + 63) / 64;
+  p.total_tiles = (n_cols + 127) / 128;
+  p.n_row_blocks = (n_rows + 127) / 128;
+  p.diag_shift = diag_shift;
+  p.w_row = w_row;
+  p.w_col = w_col;
+  p.xq = x_q;
+  p.yq = y_q;
+  p.scale_ptr = scale;
+  p.out_scale = 1.0f / (2.0f * (float)n_global) / G_SCALE;
+
+  uint8_t* ws = (uint8_t*)workspace;
+  const int npx = p.n_row_blocks * 128, npy = p.total_tiles * 128;
+  float* xmax = (float*)ws;
+  ws += align256((size_t)npx * 4);
+  float* xlg = (float*)ws;
+  ws += align256((size_t)npx * 4);
+  float* ymax = (float*)ws;
+  ws += align256((size_t)npy * 4);
+  float* ylg = (float*)ws;
+  ws += align256((size_t)npy * 4);
+  float* xr = (float*)ws;
+  ws += align256((size_t)npx * 4);
+  float* yc = (float*)ws;
+  ws += align256((size_t)npy * 4);
+  float* range_part = (float*)ws;
+  int* fast_flag = (int*)(ws + 256);
+  uint8_t* base = (uint8_t*)workspace;
+  float* ds_part = (float*)(base + L.off_ds);
+  p.dx = dx;
+  p.part = (float*)(base + L.off_parts);
+  p.dx_bf16 = dx_bf16;
+  p.out_mul = out_mul;
+  p.xmax = xmax;
+  p.xlg = xlg;
+  p.ymax = ymax;
+  p.ylg = ylg;
+  p.xr = xr;
+  p.yc = yc;
+  p.fast_flag = fast_flag;
+  p.ds_part = dscale ? ds_part : nullptr;
+  P.dy = dy;
+  P.dy_bf16 = dy_owner_rows ? 0 : dy_bf16;
+  P.dy_mul = dy_owner_rows ? nullptr : out_mul;
+  P.dy_scatter = dy_sc;
+  P.dy_part = (float*)(base + L.off_dy_part);
+  P.gring = base + L.off_ring;
+  int* flags = (int*)(base + L.off_flags);
+  P.ready = flags;
+  P.done_i = flags + (size_t)L.np * GB_FLAG_STRIDE;
+  P.done_t = P.done_i + (size_t)L.np * GB_RING_DEPTH * GB_FLAG_STRIDE;
+  P.col_turn = P.done_t + (size_t)L.np * GB_RING_DEPTH * GB_FLAG_STRIDE;
+  P.np = L.np;
+  P.s = L.s;
+  P.dy_direct = (dy != nullptr && !dy_owner_rows && !dy_bf16) ? 1 : 0;
+  p.wait_prof = wait_prof_buffer();
+
+  const float l2wr = log2f(w_row), l2wc = log2f(w_col);
+  const int force_slow = (w_row == 0.f || w_col == 0.f) ? 1 : 0;
+  lse_range_kernel<<<RANGE_BLOCKS, 256, 0, stream>>>(x_max, x_lg2l, n_rows, l2wr, y_max, y_lg2l,
+                                                     n_cols, l2wc, scale, range_part);
+  VLP_COUNT_LAUNCH(1);
+  stats_pad_kernel<<<(npx + 255) / 256, 256, 0, stream>>>(x_max, x_lg2l, n_rows, npx, l2wr, scale,
+                                                          1.f, range_part, force_slow, fast_flag,
+                                                          xmax, xlg, xr);
+  VLP_COUNT_LAUNCH(1);
+  stats_pad_kernel<<<(npy + 255) / 256, 256, 0, stream>>>(y_max, y_lg2l, n_cols, npy, l2wc, scale,
+                                                          -1.f, range_part, force_slow, fast_flag,
+                                                          ymax, ylg, yc);
+  VLP_COUNT_LAUNCH(1);
+  VLP_CUDA_OK(cudaGetLastError());
+
+  CUtensorMap map_k, map_mn, map_xmn;
+  rc = make_tmap_sw128(&map_k, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
+  if (rc) return rc;
+  rc = make_tmap_sw128(&map_mn, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 64);
+  if (rc) return rc;
+  rc = make_tmap_sw128(&map_xmn, x, 2, (uint64_t)d, (uint64_t)n_rows, (uint64_t)ldx, 64);
+  if (rc) return rc;
+  // the dT sums leave through TMA tile stores / reduce-adds: 32 x 32 fp32 boxes of dy (direct) or dy_part
+  CUtensorMap map_dy;
+  rc = make_tmap_sw128(&map_dy, P.dy_direct ? dy : (void*)P.dy_part, 4, (uint64_t)d, (uint64_t)n_cols,
+                       (uint64_t)d, 32, true);
+  if (rc) return rc;
+
+  VLP_CUDA_OK(set_smem_attr_once((const void*)grad_both_kernel, GB_SMEM, 1));
+  const int n_pass = p.kblocks > 8 ? 2 : 1;
+  const int per_pass = (p.kblocks + n_pass - 1) / n_pass;
+  float* ds_keep = p.ds_part;
+  KernelTimer& kt = kernel_timer();
+  if (kt.enabled) VLP_CUDA_OK(cudaEventRecord(kt.e0, stream));
+  for (int pass = 0; pass < n_pass; ++pass) {
+    p.db0 = pass * per_pass;
+    p.ndb = (p.kblocks - p.db0) < per_pass ? (p.kblocks - p.db0) : per_pass;
+    p.ds_part = pass == 0 ? ds_keep : nullptr;
+    VLP_CUDA_OK(cudaMemsetAsync(flags, 0, L.flag_bytes, stream));
+    grad_both_kernel<<<2 * L.np + L.nq, GB_THREADS, GB_SMEM, stream>>>(map_k, map_mn, map_xmn, map_dy, P);
+    VLP_COUNT_LAUNCH(1);
+  }
+  if (kt.enabled) {
+    VLP_CUDA_OK(cudaEventRecord(kt.e1, stream));
+    kt.pending = true;
+  }
+  VLP_CUDA_OK(cudaGetLastError());
+  for (int pi = 0; pi < L.s.n_ph; ++pi) {
+    const SchedPhase& ph = L.s.ph[pi];
+    if (ph.n_seg <= 1) continue;
+    dx_seg_reduce_kernel<<<dim3(ph.n_rows, RED_SPLIT), 256, 0, stream>>>(
+        p.part, ph, n_rows, d, out_mul, dx_bf16, dx, p.scatter);
+    VLP_COUNT_LAUNCH(1);
+    VLP_CUDA_OK(cudaGetLastError());
+  }
+  if (dscale) {
+    ds_reduce_kernel<<<1, 256, 0, stream>>>(ds_part, L.np * GB_SMX_WARPS,
+                                            1.0f / (2.0f * (float)n_global), dscale);
+    VLP_COUNT_LAUNCH(1);
+    VLP_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// host-only: the schedule of the single-recompute backward for np producer slots / nq dT consumers.
+// info = {phases, steps, dI partial slots, runs, waves, np, nq, 0}; prod rows = {slot, step, row
+// block, column tile, dI partial slot or -1}; cons rows = {consumer, slot, step, row block, column
+// tile, rank of the piece in its column, pieces of the column}, in the order each consumer works.
+int vlpclip_grad_both_plan(int n_row_blocks, int n_col_tiles, int np, int nq, int* info, int* prod,
+                           int max_prod, int* n_prod, int* cons, int max_cons, int* n_cons) {
+  if (n_row_blocks <= 0 || n_col_tiles <= 0 || !info || !prod || !cons || !n_prod || !n_cons)
+    return fail(-1, "grad_both_plan: bad arguments");
+  if (np <= 0 || nq <= 0) {
+    const int n_sms = usable_sms();
+    if (!gb_roles(n_sms > 0 ? n_sms : 148, &np, &nq)) return fail(-1, "grad_both_plan: too few SMs");
+  }
+  if (nq < np) return fail(-1, "grad_both_plan: need nq >= np (got %d < %d)", nq, np);
+  const Sched s = make_sched(n_row_blocks, n_col_tiles, np, nq);
+  info[0] = s.n_ph; info[1] = s.t_total; info[2] = s.n_parts; info[3] = s.n_runs;
+  info[4] = s.n_waves; info[5] = s.np; info[6] = s.nq; info[7] = 0;
+  int npd = 0, ncs = 0;
+  for (int a = 0; a < s.np; ++a)
+    for (int pi = 0; pi < s.n_ph; ++pi) {
+      const SchedPhase& ph = s.ph[pi];
+      for (int w = 0; w < ph.n_waves; ++w) {
+        VRow vr;
+        if (!sched_vrow(s, ph, w, a, vr)) continue;
+        for (int u = 0; u < ph.cs; ++u) {
+          const int col = sched_col(ph, vr, a, u);
+          if (col < 0) continue;
+          if (npd >= max_prod) return fail(-1, "grad_both_plan: producer buffer too small");
+          int* o = prod + 5 * npd++;
+          o[0] = a; o[1] = ph.t0 + w * ph.cs + u; o[2] = vr.rb; o[3] = col; o[4] = vr.part;
+        }
+      }
+    }
+  for (int q = 0; q < s.nq; ++q) {
+    PieceIter it(s, q);
+    Piece pc;
+    while (it.next(pc)) {
+      int rank, total;
+      sched_piece_rank(s, pc.col, pc.gw, pc.wrapped, rank, total);
+      for (int a = pc.a_hi; a >= pc.a_lo; --a) {
+        if (ncs >= max_cons) return fail(-1, "grad_both_plan: consumer buffer too small");
+        int* o = cons + 7 * ncs++;
+        o[0] = q; o[1] = a; o[2] = pc.t_hi + (pc.a_hi - a); o[3] = pc.rb_hi - (pc.a_hi - a);
+        o[4] = pc.col; o[5] = rank; o[6] = total;
+      }
+    }
+  }
+  *n_prod = npd;
+  *n_cons = ncs;
+  return 0;
 }
 
 // out = mul * (slot 0 + slot 1 + ... ) in slot order: the local half of the fused reduce-scatter

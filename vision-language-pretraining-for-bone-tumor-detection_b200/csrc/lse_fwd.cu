@@ -628,14 +628,8 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   if (rc) return rc;
 
   const size_t smem = FWD_STAGES * FWD_STAGE_BYTES + sizeof(FwdBarriers) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VLP_CUDA_OK(cudaFuncSetAttribute(lse_partial_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  VLP_CUDA_OK(set_smem_attr_once((const void*)lse_partial_kernel<false>, (int)smem, 2));
+  VLP_CUDA_OK(set_smem_attr_once((const void*)lse_partial_kernel<true>, (int)smem, 3));
   const int n_items = p.n_row_blocks * p.n_chunks;
   const int grid = n_items < nsm ? n_items : nsm;
   if (fused)

@@ -280,12 +280,7 @@ static int launch_gemm_kmajor(const float* a, const float* b, int m, int n, int 
   p.n = n;
   p.k = k;
   const size_t smem = PG_STAGES * PG_STAGE_BYTES + sizeof(PgBarriers) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLP_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    attr_set = true;
-  }
+  VLP_CUDA_OK(set_smem_attr_once((const void*)gemm_tf32_kernel, (int)smem, 4));
   dim3 grid((m + 127) / 128, (n + p.n_tile - 1) / p.n_tile, p.n_splits);
   gemm_tf32_kernel<<<grid, PG_THREADS, smem, stream>>>(map_a, map_b, p);
   VLP_COUNT_LAUNCH(1);

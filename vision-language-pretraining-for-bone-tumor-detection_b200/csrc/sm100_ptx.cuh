@@ -203,6 +203,46 @@ VLP_DEVICE void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// 1D bulk copies (no tensor map): byte images move unchanged, so a 128B-swizzled smem tile can
+// travel smem -> global -> smem of another SM and still match its UMMA descriptor.
+VLP_DEVICE void bulk_store_1d(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+VLP_DEVICE void bulk_load_1d(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// orders generic-proxy and async-proxy (TMA / bulk copy) accesses of this thread, all state spaces
+VLP_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------
+// global-memory flags between persistent CTAs (gpu scope)
+// ----------------------------------------------------------------------------
+VLP_DEVICE int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+VLP_DEVICE void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+VLP_DEVICE void st_relaxed_gpu(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+VLP_DEVICE float4 ld_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ----------------------------------------------------------------------------

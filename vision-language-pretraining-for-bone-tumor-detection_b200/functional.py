@@ -22,6 +22,9 @@ import torch
 from . import _lib, sharded
 
 LOGIT_SCALE_MAX = 100.0  # reference: torch.clamp(logit_scale.exp(), max=100)  (:457)
+# VLP_B200_SINGLE_SWEEP=0: two grad_pair_kernel passes (dI, dT; S recomputed per direction) instead
+# of the single-recompute vlpclip_grad_both kernel
+SINGLE_SWEEP = os.environ.get("VLP_B200_SINGLE_SWEEP", "1") != "0"
 # VLP_B200_EXACT_COLUMNS=1: give the column statistics their own sweep (exact column maxima)
 # instead of fusing them into the row sweep (see include/vlpclip.h: vlpclip_lse_fwd_fused)
 EXACT_COLUMNS = os.environ.get("VLP_B200_EXACT_COLUMNS", "0") == "1"
@@ -233,6 +236,47 @@ def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_globa
                           ds.data_ptr() if want_dscale else None, ws.data_ptr(), nbytes, _stream())
     _lib.check(rc, "grad")
     return dx, ds
+
+
+def _grad_both(x_f16, y_f16, x_stats, y_stats, scale, diag_shift: int, n_global: int,
+               w_row: float = 1.0, w_col: float = 1.0, want_dscale: bool = False,
+               out_mul: Optional[torch.Tensor] = None, out_dtypes=(torch.float32, torch.float32),
+               window: "Optional[PeerWindow]" = None):
+    """Single-recompute backward: (dX, dY | parity, dscale) from ONE sweep over the logit tiles.
+
+    Without ``window`` dY is returned as a tensor; with a peer window the final dY rows are stored
+    into the owning ranks' windows (fused reduce-scatter) and the window parity is returned instead
+    (finish with ``_scatter_finish`` after a collective)."""
+    lib = _lib.load()
+    n_rows, d = x_f16.shape
+    n_cols = y_f16.shape[0]
+    dev = x_f16.device
+    sc = as_scale_tensor(scale, dev)
+    assert out_dtypes[0] in (torch.float32, torch.bfloat16) and out_dtypes[1] in (torch.float32, torch.bfloat16)
+    dx = torch.empty(n_rows, d, dtype=out_dtypes[0], device=dev)
+    ds = torch.zeros(1, dtype=torch.float32, device=dev) if want_dscale else None
+    nbytes = lib.vlpclip_grad_both_workspace_bytes(n_rows, n_cols, d)
+    ws = _ws(nbytes, dev)
+    if window is None:
+        dy = torch.empty(n_cols, d, dtype=out_dtypes[1], device=dev)
+        owners, n_owners, rows_per_owner, second = None, 0, 0, dy
+    else:
+        assert n_cols == window.rows * window.world and d == window.d
+        dy = None
+        parity = window.next_parity()
+        owners, n_owners, rows_per_owner, second = window.owner_rows(parity), window.world, window.rows, parity
+    rc = lib.vlpclip_grad_both(
+        x_f16.data_ptr(), x_f16.stride(0), y_f16.data_ptr(), y_f16.stride(0),
+        x_stats[0].data_ptr(), x_stats[1].data_ptr(), x_stats[2].data_ptr(),
+        y_stats[0].data_ptr(), y_stats[1].data_ptr(), y_stats[2].data_ptr(),
+        n_rows, n_cols, d, sc.data_ptr(), int(diag_shift), int(n_global), float(w_row), float(w_col),
+        out_mul.data_ptr() if out_mul is not None else None,
+        1 if out_dtypes[0] == torch.bfloat16 else 0, dx.data_ptr(),
+        1 if out_dtypes[1] == torch.bfloat16 else 0, dy.data_ptr() if dy is not None else None,
+        owners, n_owners, rows_per_owner, ds.data_ptr() if want_dscale else None, ws.data_ptr(),
+        nbytes, _stream())
+    _lib.check(rc, "grad_both")
+    return dx, second, ds
 
 
 # ----------------------------------------------------------------------------------------------
@@ -502,6 +546,12 @@ class CudaOps:
                      out_mul, out_dtype)
 
     @staticmethod
+    def grad_both(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
+                  out_mul=None, out_dtypes=(torch.float32, torch.float32), window=None):
+        return _grad_both(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
+                          want_dscale, out_mul, out_dtypes, window)
+
+    @staticmethod
     def to_backward_operand(x_bf16):
         return cast_bf16_to_f16(x_bf16)
 
@@ -618,7 +668,7 @@ class _FusedClipLoss(torch.autograd.Function):
             CudaOps, i_f16, t_all_f16, r_stats, c_stats, ctx.scale, ctx.n_loc, ctx.n_glob, ctx.rank,
             world, ctx.group, w_r, w_c, need_i, need_t, need_ls, out_mul=mul,
             out_dtypes=(kdt(ctx.in_dtypes[0]), kdt(ctx.in_dtypes[1])),
-            tail_barrier=ctx.tail_barrier)
+            tail_barrier=ctx.tail_barrier, single_sweep=SINGLE_SWEEP)
         d_ls = None
         if need_ls:
             d_ls = ds * ctx.dscale_dls                      # chain rule through exp + clamp (:456-457)
@@ -669,7 +719,7 @@ def _graph_backward(fo, g, group, needs, in_dtypes, ls_shape):
         CudaOps, fo["i_f16"], fo["t_all_f16"], plan["r_stats"], plan["c_stats"], fo["scale"],
         plan["n_loc"], plan["n_glob"], plan["rank"], plan["world"], group, 1.0, 1.0, need_i, need_t,
         need_ls, out_mul=g, out_dtypes=(_kernel_dtype(in_dtypes[0]), _kernel_dtype(in_dtypes[1])),
-        tail_barrier=plan["bwd_operands"] is not None)
+        tail_barrier=plan["bwd_operands"] is not None, single_sweep=SINGLE_SWEEP)
     d_ls = None
     if need_ls:
         d_ls = (ds * fo["dscale_dls"] * g).to(in_dtypes[2]).reshape(ls_shape)
