@@ -64,6 +64,7 @@ class ClockSampler:
         self.max_mhz = None
         self._stop = False
         self._thread = None
+        self.active = False      # samples are kept only while the timed region runs
 
     def _run(self):
         import pynvml
@@ -78,6 +79,9 @@ class ClockSampler:
         h = pynvml.nvmlDeviceGetHandleByIndex(idx)
         self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         while not self._stop:
+            if not self.active:
+                time.sleep(0.002)
+                continue
             try:
                 self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                 mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
@@ -246,13 +250,15 @@ def run_ours(args):
             torch.distributed.barrier()
             torch.cuda.synchronize()
 
-    for w in range(max(3, args.warmup)):
-        step(*sets[w % 2])
-    sync_all()
-
+    # (the NVML thread is started BEFORE the warm-up: nvmlInit contends with kernel launches for
+    #  driver locks and must not fall into the timed region; it only samples while `active`)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for w in range(max(3, args.warmup)):
+        step(*sets[w % 2])
+    sync_all()
+    sampler.active = True
     launches0 = lib.vlpclip_launch_count() + VF.GRAPH_REPLAYED_LAUNCHES
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -263,6 +269,7 @@ def run_ours(args):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+    sampler.active = False
     launches = lib.vlpclip_launch_count() + VF.GRAPH_REPLAYED_LAUNCHES - launches0
     if world > 1:
         t = torch.tensor([ms], device=dev)
