@@ -29,6 +29,10 @@ constexpr int FWD_SMW = 16;                  // softmax warps: 4 TMEM lane quart
 constexpr int FWD_CG = FWD_SMW / 4;          // column groups per tile
 constexpr int FWD_CPT = 128 / FWD_CG;        // columns per thread (32)
 constexpr int FWD_THREADS = 64 + FWD_SMW * 32;
+// warps 0..15: softmax (warp & 3 = TMEM lane quarter); the TMA and MMA warps get the highest warp ids:
+// the issue arbiter of an SM sub-partition prefers the highest id, and their issue latency is critical
+constexpr int FWD_TMA_WARP = FWD_SMW;
+constexpr int FWD_MMA_WARP = FWD_SMW + 1;
 constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: d/2 columns (256 at d = 512, 384 at d = 768)
 // S buffers of 128 columns sit at the top of TMEM: two (double buffered) while d <= 512, a single
 // one for 512 < d <= 768 (MMA and softmax of consecutive tiles then serialise)
@@ -94,8 +98,8 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     mbar_init(smem_u32(&bars->x_free), 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<1>(smem_u32(&bars->tmem_base), 512);
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_y);
+  if (warp == FWD_MMA_WARP) tmem_alloc<1>(smem_u32(&bars->tmem_base), 512);
+  if (warp == FWD_TMA_WARP && lane == 0) tma_prefetch_desc(&map_y);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -106,7 +110,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
   const uint32_t nbuf = p.kblocks <= 8 ? 2u : 1u;
   const uint32_t tmem_s_col = 512u - nbuf * 128u;
 
-  if (warp == 0) {
+  if (warp == FWD_TMA_WARP) {
     // ================= TMA producer (whole warp converged, one elected lane issues) ==========
     uint32_t it = 0;  // running stage counter
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -129,11 +133,11 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == FWD_MMA_WARP) {
     // ================= MMA issuer (whole warp converged, one elected lane issues) ===========
     const uint32_t fmt = p.operand_f16 ? UMMA_F16 : UMMA_BF16;
     const uint32_t idesc = make_idesc(fmt, fmt, MAJOR_K, MAJOR_K, 128, 128);
-    uint32_t it = 0, tile_ctr = 0, item_ctr = 0;
+    uint32_t it = 0, tile_ctr = 0, item_ctr = 0, peek = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
       const int chunk = item / p.n_row_blocks;
       const int t0 = chunk * p.tiles_per_chunk;
@@ -150,8 +154,12 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
           const uint32_t st = it % FWD_STAGES;
           const uint32_t ph = (it / FWD_STAGES) & 1;
           const int nkb = min(FWD_KB_PER_STAGE, p.kblocks - kb);
-          mbar_wait(smem_u32(&bars->full[st]), ph);
+          if (!peek) mbar_wait(smem_u32(&bars->full[st]), ph);
           tc_fence_after();
+          {   // has the NEXT ring stage landed already?  (answer arrives while the MMAs below issue)
+            const uint32_t nst = (it + 1) % FWD_STAGES, nph = ((it + 1) / FWD_STAGES) & 1;
+            peek = mbar_test_wait(smem_u32(&bars->full[nst]), nph);
+          }
           if (elect_one()) {
             for (int q = 0; q < nkb; ++q) {
               const uint32_t sb = ring + st * FWD_STAGE_BYTES + q * FWD_BOX_BYTES;
@@ -177,7 +185,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     // ================= softmax warps =================
     // thread = (row, column group): quarter = TMEM lane quarter of the warp, cg = 32-column group
     const uint32_t quarter = warp & 3;
-    const uint32_t wslot = warp - 2;             // 0 .. FWD_SMW-1
+    const uint32_t wslot = warp;                 // 0 .. FWD_SMW-1
     const uint32_t cg = wslot >> 2;
     const uint32_t row_in_blk = quarter * 32 + lane;
     const uint32_t lane_addr = (quarter * 32u) << 16;
@@ -334,7 +342,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<1>(tmem, 512);
+  if (warp == FWD_MMA_WARP) tmem_dealloc<1>(tmem, 512);
 }
 
 // Merge [nparts][n] partial (max, l) pairs in fixed order.

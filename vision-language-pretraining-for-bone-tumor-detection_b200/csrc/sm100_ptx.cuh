@@ -110,6 +110,21 @@ VLP_DEVICE uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok;
 }
+// non-blocking test (try_wait may suspend the thread): used to peek at the NEXT pipeline stage
+// before issuing the current stage's MMAs, so that its ~100-cycle latency overlaps the issue
+VLP_DEVICE uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 VLP_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
