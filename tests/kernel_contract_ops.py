@@ -76,6 +76,17 @@ class ContractOps:
         return dx, ds
 
     @staticmethod
+    def grad_both(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
+                  out_mul=None, out_dtypes=None, window=None):
+        """Contract of vlpclip_grad_both: (dX, dY, dscale) of ONE sweep; dY = G^T X is the other
+        direction's dX with the roles of X and Y (and of the weights) swapped."""
+        dx, ds = ContractOps.grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
+                                  want_dscale, out_mul)
+        dy, _ = ContractOps.grad(y, x, y_stats, x_stats, scale, -diag_shift, n_global, w_col, w_row,
+                                 False, out_mul)
+        return dx, dy, ds
+
+    @staticmethod
     def to_backward_operand(x):
         return x
 
@@ -128,6 +139,25 @@ class WindowContractOps(ContractOps):
         window.slots[window.parity] = [p[lo:lo + window.rows].clone() for p in parts]
         window.log.append("grad_scatter")
         return window.parity, ds
+
+    @classmethod
+    def grad_both(cls, x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
+                  out_mul=None, out_dtypes=None, window=None):
+        import torch.distributed as dist
+        if window is None:
+            return ContractOps.grad_both(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row,
+                                         w_col, want_dscale, out_mul)
+        dx, ds = ContractOps.grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
+                                  want_dscale, out_mul)
+        # the dY rows leave unscaled through the owners' slots (out_mul is applied by scatter_finish)
+        dy, _ = ContractOps.grad(y, x, y_stats, x_stats, scale, -diag_shift, n_global, w_col, w_row, False)
+        window.parity ^= 1
+        parts = [torch.empty_like(dy) for _ in range(window.world)]
+        dist.all_gather(parts, dy.contiguous(), group=window.group)
+        lo = window.rank * window.rows
+        window.slots[window.parity] = [p[lo:lo + window.rows].clone() for p in parts]
+        window.log.append("grad_both")
+        return dx, window.parity, ds
 
     @classmethod
     def scatter_finish(cls, window, parity, out_mul, out_dtype, device):

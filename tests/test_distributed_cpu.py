@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, d, ls, out_dir, exact, windows=False):
+def _worker(rank, world, port, n, d, ls, out_dir, exact, windows=False, single_sweep=True):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -45,11 +45,12 @@ def _worker(rank, world, port, n, d, ls, out_dir, exact, windows=False):
         mul = torch.tensor(0.5, dtype=torch.float64) if windows else None
         d_i, d_t, ds = sharded.backward_plan(ContractOps, i_loc, plan["t_all"], plan["r_stats"],
                                              plan["c_stats"], scale, b, n, rank, world, dist.group.WORLD,
-                                             out_mul=mul, tail_barrier=plan["bwd_operands"] is not None)
+                                             out_mul=mul, tail_barrier=plan["bwd_operands"] is not None,
+                                             single_sweep=single_sweep)
         if windows:
             assert plan["bwd_operands"] is not None
             log = next(iter(WindowContractOps.windows.values())).log
-            assert log == ["push_gather", "grad_scatter", "scatter_finish"], log
+            assert log == ["push_gather", "grad_both" if single_sweep else "grad_scatter", "scatter_finish"], log
             d_i, d_t = d_i / mul, d_t / mul          # out_mul scales dI and dT, never dscale
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=plan["loss"].numpy(),
                  image_loss=plan["image_loss"].numpy(), text_loss=plan["text_loss"].numpy(),
@@ -87,13 +88,15 @@ def test_sharded_plan_matches_single_process_oracle(tmp_path, world, n, d, ls, e
         assert abs(float(got["ds"][0]) - ref["dscale"]) < 1e-10 * max(1.0, abs(ref["dscale"]))
 
 
+@pytest.mark.parametrize("single_sweep", [True, False])
 @pytest.mark.parametrize("world,n,d,ls", [(2, 96, 32, 2.6593), (4, 64, 16, 3.5), (8, 64, 16, 2.6593)])
-def test_sharded_plan_with_peer_window_ops_matches_oracle(tmp_path, world, n, d, ls):
+def test_sharded_plan_with_peer_window_ops_matches_oracle(tmp_path, world, n, d, ls, single_sweep):
     """Same check through the fused-collective branches (push-gather, row scatter into owner slots,
-    slot sum in rank order, upstream gradient applied by the finishing op)."""
+    slot sum in rank order, upstream gradient applied by the finishing op), with the single-recompute
+    backward (one sweep feeds dI and the scattered dT) and with the two-pass one."""
     from oracle import clip_oracle as O
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, n, d, ls, str(tmp_path), False, True), nprocs=world,
+    mp.spawn(_worker, args=(world, port, n, d, ls, str(tmp_path), False, True, single_sweep), nprocs=world,
              join=True)
     I, T = O.make_embeddings(n, d, rho=0.35, seed=42)
     ref = O.closed_form(I.numpy(), T.numpy(), ls)
@@ -116,9 +119,11 @@ def test_single_process_plan_matches_oracle():
     ls = 2.0
     scale = math.exp(ls)
     plan = sharded.forward_plan(ContractOps, I.double(), T.double(), scale, None)
-    d_i, d_t, ds = sharded.backward_plan(ContractOps, I.double(), plan["t_all"], plan["r_stats"],
-                                         plan["c_stats"], scale, 50, 50, 0, 1, None)
     ref = O.closed_form(I.numpy(), T.numpy(), ls)
     assert abs(float(plan["loss"]) - ref["loss"]) < 1e-12
-    assert O.rel_err(d_i.numpy(), ref["dI"]) < 1e-12 and O.rel_err(d_t.numpy(), ref["dT"]) < 1e-12
-    assert abs(float(ds[0]) - ref["dscale"]) < 1e-12
+    for single_sweep in (True, False):
+        d_i, d_t, ds = sharded.backward_plan(ContractOps, I.double(), plan["t_all"], plan["r_stats"],
+                                             plan["c_stats"], scale, 50, 50, 0, 1, None,
+                                             single_sweep=single_sweep)
+        assert O.rel_err(d_i.numpy(), ref["dI"]) < 1e-12 and O.rel_err(d_t.numpy(), ref["dT"]) < 1e-12
+        assert abs(float(ds[0]) - ref["dscale"]) < 1e-12

@@ -55,6 +55,17 @@ def _worker(rank, world, port, n, d, ls, out_dir):
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss.item(), image_loss=il.item(),
                  text_loss=tl.item(), dI=Il.grad.cpu().numpy(), dT=Tl.grad.cpu().numpy(),
                  dl=lsc.grad.item(), used_peer_windows=int(any(w.ok for w in VF._PEER_WINDOWS.values())))
+        # the same step with the two-pass backward (dT kernel with the fused reduce-scatter, then the
+        # dI kernel) instead of the single-recompute kernel: identical up to fp32 summation order
+        VF.SINGLE_SWEEP, VF._GRAPH_MODE = False, "0"
+        Il.grad = Tl.grad = lsc.grad = None
+        loss1, _, _ = VF.fused_clip_loss_from_embeddings(Il, Tl, lsc, group=dist.group.WORLD)
+        loss1.backward()
+        torch.cuda.synchronize()
+        assert abs(loss1.item() - first[0]) <= 1e-6 * abs(first[0])
+        assert (Tl.grad - first[2]).norm() <= 2e-5 * first[2].norm()
+        assert (Il.grad - first[1]).norm() <= 2e-5 * first[1].norm()
+        VF.SINGLE_SWEEP = True
         # the same step with NCCL reduce-scatter instead of the fused NVLink stores: identical up
         # to the fp32 summation order of the partials
         VF.PEER_RS_MODE, VF._GRAPH_MODE = "0", "0"
@@ -73,7 +84,11 @@ def _worker(rank, world, port, n, d, ls, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,d,ls", [(2, 4096, 512, math.log(1 / 0.07)), (2, 600, 72, 3.0)])
+# BASELINE config 3 (4096 x 512 over 2 / 4 / 8 GPUs) plus ragged shards (rows per rank not a multiple
+# of the 128-row tile, K not a multiple of 64)
+@pytest.mark.parametrize("world,n,d,ls", [(2, 4096, 512, math.log(1 / 0.07)), (4, 4096, 512, math.log(1 / 0.07)),
+                                          (8, 4096, 512, math.log(1 / 0.07)), (2, 600, 72, 3.0),
+                                          (4, 1000, 72, 3.0), (8, 2408, 136, math.log(50.0))])
 def test_sharded_global_batch_matches_oracle(tmp_path, world, n, d, ls):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -1294,7 +1294,21 @@ int vlpclip_grad_both(const void* x, int ldx, const void* y, int ldy, const floa
     p.ndb = (p.kblocks - p.db0) < per_pass ? (p.kblocks - p.db0) : per_pass;
     p.ds_part = pass == 0 ? ds_keep : nullptr;
     VLP_CUDA_OK(cudaMemsetAsync(flags, 0, L.flag_bytes, stream));
-    grad_both_kernel<<<2 * L.np + L.nq, GB_THREADS, GB_SMEM, stream>>>(map_k, map_mn, map_xmn, map_dy, P);
+    {
+      // cooperative launch: the CTAs spin-wait on one another, so the grid must be co-resident as
+      // a whole (a plain launch could interleave with another persistent grid and deadlock)
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = dim3(2 * L.np + L.nq);
+      lc.blockDim = dim3(GB_THREADS);
+      lc.dynamicSmemBytes = GB_SMEM;
+      lc.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeCooperative;
+      at[0].val.cooperative = 1;
+      lc.attrs = at;
+      lc.numAttrs = 1;
+      VLP_CUDA_OK(cudaLaunchKernelEx(&lc, grad_both_kernel, map_k, map_mn, map_xmn, map_dy, P));
+    }
     VLP_COUNT_LAUNCH(1);
   }
   if (kt.enabled) {
