@@ -20,8 +20,10 @@ def VF():
     return functional
 
 
+# (30 and 37: batch sizes that are not multiples of 4 -- the reference's samplers yield remainder
+#  batches of any size and its own __main__ uses 30; dW = feat^T du then has K = 30 / 37)
 @pytest.mark.parametrize("n,fi,ft,d", [(256, 512, 312, 512), (300, 512, 768, 128), (1024, 2048, 312, 256), (64, 512, 312, 32),
-                                       (384, 512, 312, 768)])
+                                       (384, 512, 312, 768), (30, 512, 312, 128), (37, 512, 312, 64)])
 def test_head_against_straight_through_oracle(VF, n, fi, ft, d):
     dev = torch.device("cuda:0")
     ls = math.log(1 / 0.07)
@@ -53,18 +55,56 @@ def test_head_against_straight_through_oracle(VF, n, fi, ft, d):
     assert abs(lsc.grad.item() - ref["dlogit_scale"]) < 1e-3 * abs(ref["dlogit_scale"])
 
 
-def test_head_against_reference_golden(VF, golden_dir):
-    """Reference forward + _compute_loss run in fp32 (golden) vs the fused head: the loss differs
-    only by the bf16 rounding of the embeddings (<= 3e-4 relative)."""
-    g = dict(np.load(os.path.join(golden_dir, "head_n32_f512_312_d128_fp32.npz")))
+@pytest.mark.parametrize("name", ["head_n32_f512_312_d128_fp32", "head_n64_f128_40_d64_fp64",
+                                  "head_n48_f64_40_d32_clamped"])
+def test_head_against_reference_golden(VF, golden_dir, name):
+    """Outputs AND gradients of the reference's own forward + _compute_loss (golden, unrounded fp32 /
+    fp64 embeddings) vs the fused head, which evaluates the loss on bf16-rounded embeddings.  That
+    rounding alone moves the reference's gradients by 1.7-2.9e-3, so the
+    feature-level bounds are the measured ones, not the 1e-4 / 1e-3 of the embedding-level contract
+    (which test_head_against_straight_through_oracle and the embedding goldens cover): loss 5e-4,
+    gradients 5e-3 normwise.  The errors are printed (pytest -s) for the record."""
+    g = dict(np.load(os.path.join(golden_dir, name + ".npz")))
     n, f_img, f_txt, d, ls, seed, _ = g["params"]
     fi, ft, wi, wt = O.make_features(int(n), int(f_img), int(f_txt), int(d), seed=int(seed))
     dev = torch.device("cuda:0")
-    loss, il, tl, ie, te = VF.fused_clip_loss(fi.to(dev), ft.to(dev), wi.to(dev), wt.to(dev),
-                                              torch.tensor([ls], dtype=torch.float64, device=dev))
-    assert np.abs(ie.cpu().numpy() - g["image_embeddings"]).max() < 1e-3
-    assert np.abs(te.cpu().numpy() - g["text_embeddings"]).max() < 1e-3
-    assert abs(loss.item() - float(np.ravel(g["loss"])[0])) < 1e-3 * float(np.ravel(g["loss"])[0])
+    args = [t.to(dev).requires_grad_(True) for t in (fi, ft, wi, wt)]
+    lsc = torch.tensor([ls], dtype=torch.float64, device=dev, requires_grad=True)
+    loss, il, tl, ie, te = VF.fused_clip_loss(*args, lsc)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert np.abs(ie.detach().cpu().numpy() - g["image_embeddings"]).max() < 1e-3
+    assert np.abs(te.detach().cpu().numpy() - g["text_embeddings"]).max() < 1e-3
+    ref_loss = float(np.ravel(g["loss"])[0])
+    e_loss = abs(loss.item() - ref_loss) / ref_loss
+    errs = {"loss": e_loss}
+    for key, t in (("d_image_features", args[0]), ("d_text_features", args[1]),
+                   ("d_image_projection", args[2]), ("d_text_projection", args[3])):
+        errs[key] = O.rel_err(t.grad.cpu().numpy(), g[key])
+    ref_dl = float(np.ravel(g["d_logit_scale"])[0])
+    errs["d_logit_scale"] = abs(lsc.grad.item() - ref_dl) / abs(ref_dl) if ref_dl != 0 else abs(lsc.grad.item())
+    print(name, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["loss"] < 5e-4
+    for key in ("d_image_features", "d_text_features", "d_image_projection", "d_text_projection"):
+        assert errs[key] < 5e-3, (key, errs[key])
+    assert errs["d_logit_scale"] < 5e-3
+
+
+def test_full_head_is_bit_reproducible(VF):
+    """Split-K partials of dW are summed in split order (no atomics): two runs agree bit for bit."""
+    dev = torch.device("cuda:0")
+    f_i, f_t, w_i, w_t = O.make_features(4096, 512, 312, 256, seed=3)
+
+    def run():
+        args = [t.to(dev).requires_grad_(True) for t in (f_i, f_t, w_i, w_t)]
+        lsc = torch.tensor([2.6593], dtype=torch.float64, device=dev, requires_grad=True)
+        loss, *_ = VF.fused_clip_loss(*args, lsc)
+        loss.backward()
+        torch.cuda.synchronize()
+        return [loss.detach().cpu()] + [a.grad.cpu() for a in args] + [lsc.grad.cpu()]
+
+    a, b = run(), run()
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
 def test_module_training_step_end_to_end():

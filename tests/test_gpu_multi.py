@@ -55,6 +55,25 @@ def _worker(rank, world, port, n, d, ls, out_dir):
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss.item(), image_loss=il.item(),
                  text_loss=tl.item(), dI=Il.grad.cpu().numpy(), dT=Tl.grad.cpu().numpy(),
                  dl=lsc.grad.item(), used_peer_windows=int(any(w.ok for w in VF._PEER_WINDOWS.values())))
+        # gradient averaging (DDP): grad_scale = world multiplies the row-sharded gradients only;
+        # d logit_scale is already the all-reduced global total on every rank and must stay as it is
+        Il.grad = Tl.grad = lsc.grad = None
+        loss_s, _, _ = VF.fused_clip_loss_from_embeddings(Il, Tl, lsc, group=dist.group.WORLD,
+                                                          grad_scale=float(world))
+        loss_s.backward()
+        torch.cuda.synchronize()
+        assert abs(lsc.grad.item() - first[3]) <= 1e-6 * abs(first[3])
+        assert (Il.grad - world * first[1]).norm() <= 1e-6 * (world * first[1]).norm()
+        assert (Tl.grad - world * first[2]).norm() <= 1e-6 * (world * first[2]).norm()
+        if torch.cuda.device_count() > 1 and rank == 0:
+            # device guard: operands on this rank's GPU while another device is current
+            other = (rank + 1) % torch.cuda.device_count()
+            with torch.cuda.device(other):
+                a = Il.detach().clone().requires_grad_(True)
+                l_other, _, _ = VF.fused_clip_loss_from_embeddings(a, Tl.detach(), lsc.detach())
+                l_other.backward()
+            torch.cuda.synchronize(dev)
+            assert torch.isfinite(l_other) and torch.isfinite(a.grad).all()
         # the same step with the two-pass backward (dT kernel with the fused reduce-scatter, then the
         # dI kernel) instead of the single-recompute kernel: identical up to fp32 summation order
         VF.SINGLE_SWEEP, VF._GRAPH_MODE = False, "0"

@@ -152,6 +152,49 @@ def test_bitwise_reproducible(VF):
     assert np.array_equal(a["dI"], b["dI"]) and np.array_equal(a["dT"], b["dT"])
 
 
+@pytest.mark.parametrize("n,d", [(1000, 128), (3000, 768), (5000, 512)])
+def test_single_sweep_backward_matches_two_pass(VF, n, d):
+    """vlpclip_grad_both (one sweep feeds dI and dT) against two vlpclip_grad passes: same G tiles,
+    so the results agree to fp32 summation order; both are bit-reproducible."""
+    dev = torch.device("cuda:0")
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=11)
+    Ib, Tb = I.to(dev).to(torch.bfloat16), T.to(dev).to(torch.bfloat16)
+    s = 1 / 0.07
+    rm, rl, rdiag, cm, cl = VF.lse_stats_fused(Ib, Tb, s, 0)
+    r, c = VF.merge_stats(rm, rl, rdiag, s)[:3], VF.merge_stats(cm, cl, rdiag, s)[:3]
+    i16, t16 = VF.cast_bf16_to_f16(Ib), VF.cast_bf16_to_f16(Tb)
+    dI2, ds2 = VF._grad(i16, t16, r, c, s, 0, n, 1.0, 1.0, True)
+    dT2, _ = VF._grad(t16, i16, c, r, s, 0, n, 1.0, 1.0, False)
+    dI, dT, ds = VF._grad_both(i16, t16, r, c, s, 0, n, 1.0, 1.0, True)
+    dIb, dTb, dsb = VF._grad_both(i16, t16, r, c, s, 0, n, 1.0, 1.0, True)
+    torch.cuda.synchronize()
+    assert torch.equal(dI, dIb) and torch.equal(dT, dTb) and torch.equal(ds, dsb)
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
+    assert rel(dI, dI2) < 2e-5 and rel(dT, dT2) < 2e-5
+    assert abs(ds.item() - ds2.item()) <= 1e-5 * abs(ds2.item())
+
+
+def test_single_sweep_backward_bf16_outputs_and_upstream_gradient(VF):
+    """bf16 gradient outputs take the partial-buffer path of the dT consumers (pieces collect in fp32,
+    the last piece reads them back); an upstream gradient is folded into the epilogues."""
+    dev = torch.device("cuda:0")
+    n, d = 3000, 256
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=12)
+    Ib, Tb = I.to(dev).to(torch.bfloat16), T.to(dev).to(torch.bfloat16)
+    s = 1 / 0.07
+    rm, rl, rdiag, cm, cl = VF.lse_stats_fused(Ib, Tb, s, 0)
+    r, c = VF.merge_stats(rm, rl, rdiag, s)[:3], VF.merge_stats(cm, cl, rdiag, s)[:3]
+    i16, t16 = VF.cast_bf16_to_f16(Ib), VF.cast_bf16_to_f16(Tb)
+    mul = torch.tensor([0.37], dtype=torch.float32, device=dev)
+    dI, dT, _ = VF._grad_both(i16, t16, r, c, s, 0, n, 1.0, 1.0, False)
+    dIh, dTh, _ = VF._grad_both(i16, t16, r, c, s, 0, n, 1.0, 1.0, False, mul,
+                                (torch.bfloat16, torch.bfloat16))
+    torch.cuda.synchronize()
+    assert dIh.dtype == torch.bfloat16 and dTh.dtype == torch.bfloat16
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()  # noqa: E731
+    assert rel(dIh, 0.37 * dI) < 4e-3 and rel(dTh, 0.37 * dT) < 4e-3      # bf16 rounding of the outputs
+
+
 def test_errors_are_raised_not_swallowed(VF):
     dev = torch.device("cuda:0")
     I, T = O.make_embeddings(16, 16)

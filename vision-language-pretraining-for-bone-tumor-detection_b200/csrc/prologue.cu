@@ -28,9 +28,9 @@ struct GemmParams {
   int n_tile;           // columns per CTA (<= 512, multiple of 16)
   int k_per_split;      // multiple of 32
   int n_splits;
-  float* c;             // [m, n] row-major
+  float* c;             // [m, n] row-major (split-K: slab `blockIdx.z` of [n_splits][m, n] partials)
   int ldc;
-  int atomic_out;       // split-K: red.add into zeroed C
+  size_t split_stride;  // elements between the partial slabs of split-K (0: no split)
   // fused normalise epilogue (n_tile covers all of n, no split-K)
   int normalize;
   float* emb_f32;
@@ -82,11 +82,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a,   // box {32 k, 128 
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
+  // (TMA and MMA are issued by converged warps under elect.sync: a lane-predicated region makes
+  //  ptxas wrap every UTMALDG / UTCHMMA in a uniformisation loop)
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < kiters; ++it) {
-        const uint32_t st = it % PG_STAGES, ph = (it / PG_STAGES) & 1;
-        mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+    for (int it = 0; it < kiters; ++it) {
+      const uint32_t st = it % PG_STAGES, ph = (it / PG_STAGES) & 1;
+      mbar_wait(smem_u32(&bars->empty[st]), ph ^ 1);
+      if (elect_one()) {
         const uint32_t sa = ring + st * PG_STAGE_BYTES, sb = sa + PG_A_BYTES;
         const uint32_t bytes = PG_A_BYTES + (n_pad > 256 ? 2 : 1) * 256 * 128;
         mbar_expect_tx(smem_u32(&bars->full[st]), bytes);
@@ -95,15 +97,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a,   // box {32 k, 128 
         if (n_pad > 256)
           tma_load_2d(sb + 256 * 128, &map_b, smem_u32(&bars->full[st]), k0 + it * 32, n0 + 256);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_lo = make_idesc(UMMA_TF32, UMMA_TF32, MAJOR_K, MAJOR_K, 128, n_lo);
-      const uint32_t idesc_hi = make_idesc(UMMA_TF32, UMMA_TF32, MAJOR_K, MAJOR_K, 128, n_hi);
-      for (int it = 0; it < kiters; ++it) {
-        const uint32_t st = it % PG_STAGES, ph = (it / PG_STAGES) & 1;
-        mbar_wait(smem_u32(&bars->full[st]), ph);
-        tc_fence_after();
+    const uint32_t idesc_lo = make_idesc(UMMA_TF32, UMMA_TF32, MAJOR_K, MAJOR_K, 128, n_lo);
+    const uint32_t idesc_hi = make_idesc(UMMA_TF32, UMMA_TF32, MAJOR_K, MAJOR_K, 128, n_hi);
+    for (int it = 0; it < kiters; ++it) {
+      const uint32_t st = it % PG_STAGES, ph = (it / PG_STAGES) & 1;
+      mbar_wait(smem_u32(&bars->full[st]), ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t sa = ring + st * PG_STAGE_BYTES, sb = sa + PG_A_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 8 fp32 = 32 B)
@@ -115,8 +118,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a,   // box {32 k, 128 
         }
         umma_commit<1>(smem_u32(&bars->empty[st]));
       }
-      umma_commit<1>(smem_u32(&bars->acc_full));
+      __syncwarp();
     }
+    if (elect_one()) umma_commit<1>(smem_u32(&bars->acc_full));
+    __syncwarp();
   } else {
     // ---- epilogue: thread == output row ----
     const uint32_t quarter = warp & 3;
@@ -184,20 +189,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a,   // box {32 k, 128 
       }
     } else {
       const bool row_ok = row < p.m;
-      float* orow = p.c + (row_ok ? (size_t)row : 0) * p.ldc + n0;
+      // split-K partials go to their own slab and are summed in split order afterwards
+      // (splitk_reduce_kernel): no atomics, so dW is bit-reproducible
+      float* orow = p.c + (size_t)blockIdx.z * p.split_stride + (row_ok ? (size_t)row : 0) * p.ldc + n0;
       for (int c = 0; c < n_pad; c += 16) {
         uint32_t v[16];
         tmem_ld_x16(tmem + lane_addr + c, v);   // warp-collective: never under a lane predicate
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (row_ok && c + j < n_cols) {
-            const float x = __uint_as_float(v[j]);
-            if (p.atomic_out)
-              atomicAdd(orow + c + j, x);
-            else
-              orow[c + j] = x;
-          }
+          if (row_ok && c + j < n_cols) orow[c + j] = __uint_as_float(v[j]);
         }
       }
     }
@@ -207,9 +208,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a,   // box {32 k, 128 
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
 }
 
-// out[c][r] = in[r][c]
+// out[c][r] = in[r][c]; rows of `out` are `ldo` >= rows floats apart (the pad is never read: the
+// tensor maps give the true K extent and TMA zero-fills beyond it)
 __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
-                                     int cols) {
+                                     int cols, int ldo) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -219,7 +221,7 @@ __global__ void transpose_f32_kernel(const float* __restrict__ in, float* __rest
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    if (c < cols && r < rows) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
   }
 }
 
@@ -267,14 +269,15 @@ __global__ void normalize_fwd_kernel(float* __restrict__ emb, __nv_bfloat16* __r
 
 static size_t pg_align(size_t x) { return (x + 255) & ~size_t(255); }
 
-// C[m,n] (+)= A[m,k] * B[n,k]^T with both operands K-major fp32
-static int launch_gemm_kmajor(const float* a, const float* b, int m, int n, int k, GemmParams p,
-                              cudaStream_t stream) {
-  if (k % 4 != 0) return fail(-1, "gemm: K (%d) must be a multiple of 4 (16-byte row stride)", k);
+// C[m,n] = A[m,k] * B[n,k]^T with both operands K-major fp32 (row strides lda / ldb floats, multiples of 4)
+static int launch_gemm_kmajor(const float* a, int lda, const float* b, int ldb, int m, int n, int k,
+                              GemmParams p, cudaStream_t stream) {
+  if (lda % 4 != 0 || ldb % 4 != 0)
+    return fail(-1, "gemm: operand row strides (%d, %d) must be multiples of 4 floats (16 bytes)", lda, ldb);
   CUtensorMap map_a, map_b;
-  int rc = make_tmap_sw128(&map_a, a, 4, (uint64_t)k, (uint64_t)m, (uint64_t)k, 128);
+  int rc = make_tmap_sw128(&map_a, a, 4, (uint64_t)k, (uint64_t)m, (uint64_t)lda, 128);
   if (rc) return rc;
-  rc = make_tmap_sw128(&map_b, b, 4, (uint64_t)k, (uint64_t)n, (uint64_t)k, 256);
+  rc = make_tmap_sw128(&map_b, b, 4, (uint64_t)k, (uint64_t)n, (uint64_t)ldb, 256);
   if (rc) return rc;
   p.m = m;
   p.n = n;
@@ -288,10 +291,46 @@ static int launch_gemm_kmajor(const float* a, const float* b, int m, int n, int 
   return 0;
 }
 
-static void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t stream) {
+static void launch_transpose(const float* in, float* out, int rows, int cols, int ldo, cudaStream_t stream) {
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  transpose_f32_kernel<<<grid, block, 0, stream>>>(in, out, rows, cols);
+  transpose_f32_kernel<<<grid, block, 0, stream>>>(in, out, rows, cols, ldo);
   VLP_COUNT_LAUNCH(1);
+}
+
+// c[i] = sum over the split-K partial slabs in split order (fixed order => bit-reproducible)
+__global__ void splitk_reduce_kernel(const float4* __restrict__ part, int n_splits, size_t stride4,
+                                     size_t n4, float4* __restrict__ c) {
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+    float4 a = part[i];
+    for (int s = 1; s < n_splits; ++s) {
+      const float4 b = part[(size_t)s * stride4 + i];
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    c[i] = a;
+  }
+}
+
+// tiling of the generic GEMM: columns per CTA, K per split, number of splits
+static void gemm_plan(int m, int n, int k, int* n_tile, int* kps_out, int* splits_out) {
+  *n_tile = n >= 512 ? 512 : ((n + 15) & ~15);
+  const int tiles = ((m + 127) / 128) * ((n + *n_tile - 1) / *n_tile);
+  int splits = 1;
+  int nsm = sm_count();
+  if (nsm <= 0) nsm = 148;
+  if (tiles < nsm / 2 && k >= 1024) {
+    splits = nsm / tiles;
+    const int max_splits = k / 512;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int kps = (k + splits - 1) / splits;
+  kps = (kps + 31) & ~31;
+  *kps_out = kps;
+  *splits_out = (k + kps - 1) / kps;
 }
 
 }  // namespace vlp
@@ -321,7 +360,7 @@ int vlpclip_project_normalize_fwd(const float* feat, const float* w, int n, int 
   if (workspace_bytes < vlpclip_project_workspace_bytes(n, f, d))
     return fail(-1, "project: workspace too small");
   float* wt = (float*)workspace;                 // W^T [d][f]: K-major B operand
-  launch_transpose(w, wt, f, d, stream);
+  launch_transpose(w, wt, f, d, f, stream);
   VLP_CUDA_OK(cudaGetLastError());
   GemmParams p = {};
   if (d > 512) {
@@ -331,7 +370,7 @@ int vlpclip_project_normalize_fwd(const float* feat, const float* w, int n, int 
     p.n_splits = 1;
     p.c = emb_f32;
     p.ldc = d;
-    int rc2 = launch_gemm_kmajor(feat, wt, n, d, f, p, stream);
+    int rc2 = launch_gemm_kmajor(feat, f, wt, f, n, d, f, p, stream);
     if (rc2) return rc2;
     normalize_fwd_kernel<<<(n + 7) / 8, 256, 0, stream>>>(emb_f32, (__nv_bfloat16*)emb_bf16,
                                                           (__half*)emb_f16, inv_norm, n, d);
@@ -347,7 +386,7 @@ int vlpclip_project_normalize_fwd(const float* feat, const float* w, int n, int 
   p.emb_bf16 = (__nv_bfloat16*)emb_bf16;
   p.emb_f16 = (__half*)emb_f16;
   p.inv_norm = inv_norm;
-  return launch_gemm_kmajor(feat, wt, n, d, f, p, stream);
+  return launch_gemm_kmajor(feat, f, wt, f, n, d, f, p, stream);
 }
 
 int vlpclip_normalize_bwd(const float* emb_f32, const float* d_emb, const float* inv_norm, int n,
@@ -363,7 +402,11 @@ int vlpclip_normalize_bwd(const float* emb_f32, const float* d_emb, const float*
 
 size_t vlpclip_gemm_workspace_bytes(int m, int n, int k) {
   if (m <= 0 || n <= 0 || k <= 0) return 0;
-  return pg_align((size_t)m * k * 4) + pg_align((size_t)n * k * 4);
+  const size_t kp = (size_t)((k + 3) & ~3);
+  int n_tile, kps, splits;
+  gemm_plan(m, n, k, &n_tile, &kps, &splits);
+  const size_t slabs = splits > 1 ? pg_align((size_t)splits * m * n * 4) : 0;
+  return pg_align((size_t)m * kp * 4) + pg_align((size_t)n * kp * 4) + slabs;
 }
 
 int vlpclip_gemm_tf32(const float* a, const float* b, float* c, int m, int n, int k, int trans_a,
@@ -375,40 +418,56 @@ int vlpclip_gemm_tf32(const float* a, const float* b, float* c, int m, int n, in
   if (rc) return rc;
   if (workspace_bytes < vlpclip_gemm_workspace_bytes(m, n, k))
     return fail(-1, "gemm: workspace too small");
+  // operands that are not K-major in memory are transposed into the workspace with their K
+  // extent padded to a multiple of 4 floats: any K works there (dW = feat^T du has K = batch size,
+  // and the reference's sampler yields remainder batches of arbitrary size)
+  const int kp = (k + 3) & ~3;
   const float* a_k = a;
   const float* b_k = b;
+  int lda = k, ldb = k;
   float* ws_a = (float*)workspace;
-  float* ws_b = (float*)((uint8_t*)workspace + pg_align((size_t)m * k * 4));
+  float* ws_b = (float*)((uint8_t*)workspace + pg_align((size_t)m * kp * 4));
+  float* ws_slab = (float*)((uint8_t*)ws_b + pg_align((size_t)n * kp * 4));
   if (trans_a) {  // given [k][m] -> need [m][k]
-    launch_transpose(a, ws_a, k, m, stream);
+    launch_transpose(a, ws_a, k, m, kp, stream);
     a_k = ws_a;
+    lda = kp;
   }
   if (!trans_b) {  // given [k][n] -> need [n][k]
-    launch_transpose(b, ws_b, k, n, stream);
+    launch_transpose(b, ws_b, k, n, kp, stream);
     b_k = ws_b;
+    ldb = kp;
   }
   VLP_CUDA_OK(cudaGetLastError());
+  if ((lda % 4) != 0 || (ldb % 4) != 0)
+    return fail(-1, "gemm: K (%d) must be a multiple of 4 for an operand that is already K-major", k);
   GemmParams p = {};
-  p.n_tile = n >= 512 ? 512 : ((n + 15) & ~15);
-  const int tiles = ((m + 127) / 128) * ((n + p.n_tile - 1) / p.n_tile);
-  int splits = 1;
-  const int nsm = sm_count();
-  if (tiles < nsm / 2 && k >= 1024) {
-    splits = nsm / tiles;
-    const int max_splits = k / 512;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-  }
-  int kps = (k + splits - 1) / splits;
-  kps = (kps + 31) & ~31;
-  splits = (k + kps - 1) / kps;
+  int kps, splits;
+  gemm_plan(m, n, k, &p.n_tile, &kps, &splits);
   p.k_per_split = kps;
   p.n_splits = splits;
-  p.c = c;
   p.ldc = n;
-  p.atomic_out = splits > 1;
-  if (p.atomic_out) VLP_CUDA_OK(cudaMemsetAsync(c, 0, (size_t)m * n * sizeof(float), stream));
-  return launch_gemm_kmajor(a_k, b_k, m, n, k, p, stream);
+  if (splits > 1) {
+    p.c = ws_slab;
+    p.split_stride = (size_t)m * n;
+  } else {
+    p.c = c;
+    p.split_stride = 0;
+  }
+  rc = launch_gemm_kmajor(a_k, lda, b_k, ldb, m, n, k, p, stream);
+  if (rc) return rc;
+  if (splits > 1) {
+    const size_t mn = (size_t)m * n;
+    if (mn % 4 != 0 || (reinterpret_cast<uintptr_t>(c) & 15) != 0)
+      return fail(-1, "gemm: split-K needs m*n %% 4 == 0 and a 16-byte aligned C");
+    int blocks = (int)((mn / 4 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>((const float4*)ws_slab, splits, mn / 4, mn / 4,
+                                                     (float4*)c);
+    VLP_COUNT_LAUNCH(1);
+    VLP_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -49,6 +49,23 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _device_guard(*tensors):
+    """Context manager making the tensors' device current: the C side launches on the current
+    device / stream (cudaGetDevice), so operands on cuda:1 while cuda:0 is current would launch on
+    the wrong GPU.  All tensor operands must share one device."""
+    dev = None
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise ValueError(f"operands live on different devices ({dev} and {t.device})")
+    if dev is None:
+        import contextlib
+        return contextlib.nullcontext()
+    return torch.cuda.device(dev)
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -631,6 +648,11 @@ class _FusedClipLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, g_il, g_tl):
+        with _device_guard(ctx.saved_tensors[0]):
+            return _FusedClipLoss._backward(ctx, g_loss, g_il, g_tl)
+
+    @staticmethod
+    def _backward(ctx, g_loss, g_il, g_tl):
         i_bf16, t_all_bf16, r_max, r_lg, r_q, c_max, c_lg, c_q = ctx.saved_tensors
         r_stats, c_stats = (r_max, r_lg, r_q), (c_max, c_lg, c_q)
         need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
@@ -662,7 +684,11 @@ class _FusedClipLoss(torch.autograd.Function):
         t_all_f16 = t_f16 if t_f16 is not None else CudaOps.to_backward_operand(t_all_bf16)
         world = ctx.world
         gs = ctx.grad_scale
-        mul = (mul.detach().float().reshape(1) * gs).contiguous()   # device scalar, no host sync
+        # grad_scale (world size under DDP averaging) applies to the ROW-SHARDED gradients only:
+        # d logit_scale is all-reduced to the global total on every rank, so averaging identical
+        # values over ranks already leaves the true gradient
+        mul_ls = mul.detach().float().reshape(1)
+        mul = (mul_ls * gs).contiguous()   # device scalar, no host sync
         kdt = lambda dt: dt if dt in (torch.float32, torch.bfloat16) else torch.float32  # noqa: E731
         d_i, d_t, ds = sharded.backward_plan(
             CudaOps, i_f16, t_all_f16, r_stats, c_stats, ctx.scale, ctx.n_loc, ctx.n_glob, ctx.rank,
@@ -672,7 +698,7 @@ class _FusedClipLoss(torch.autograd.Function):
         d_ls = None
         if need_ls:
             d_ls = ds * ctx.dscale_dls                      # chain rule through exp + clamp (:456-457)
-            d_ls = (d_ls * mul).to(ctx.in_dtypes[2]).reshape(ctx.ls_shape)
+            d_ls = (d_ls * mul_ls).to(ctx.in_dtypes[2]).reshape(ctx.ls_shape)
         if need_i and d_i.dtype != ctx.in_dtypes[0]:
             d_i = d_i.to(ctx.in_dtypes[0])
         if need_t and d_t.dtype != ctx.in_dtypes[1]:
@@ -711,8 +737,9 @@ def _graph_forward(i_bf16, t_bf16, logit_scale, group, needs):
     return out
 
 
-def _graph_backward(fo, g, group, needs, in_dtypes, ls_shape):
-    """Backward half: final gradients (upstream gradient ``g`` folded into the kernel epilogues)."""
+def _graph_backward(fo, g, g_ls, group, needs, in_dtypes, ls_shape):
+    """Backward half: final gradients (upstream gradient ``g`` = g_loss * grad_scale folded into the
+    kernel epilogues; ``g_ls`` = g_loss alone multiplies d logit_scale, see _FusedClipLoss.backward)."""
     plan = fo["plan"]
     need_i, need_t, need_ls = needs
     d_i, d_t, ds = sharded.backward_plan(
@@ -722,7 +749,7 @@ def _graph_backward(fo, g, group, needs, in_dtypes, ls_shape):
         tail_barrier=plan["bwd_operands"] is not None, single_sweep=SINGLE_SWEEP)
     d_ls = None
     if need_ls:
-        d_ls = (ds * fo["dscale_dls"] * g).to(in_dtypes[2]).reshape(ls_shape)
+        d_ls = (ds * fo["dscale_dls"] * g_ls).to(in_dtypes[2]).reshape(ls_shape)
     if d_i is not None and d_i.dtype != in_dtypes[0]:
         d_i = d_i.to(in_dtypes[0])
     if d_t is not None and d_t.dtype != in_dtypes[1]:
@@ -742,6 +769,7 @@ class _GraphEntry:
         self.ls = torch.zeros(1, dtype=in_dtypes[2] if in_dtypes[2] == torch.float64
                               else torch.float32, device=device)
         self.g = torch.ones(1, dtype=torch.float32, device=device)   # upstream gradient * grad_scale
+        self.g_ls = torch.ones(1, dtype=torch.float32, device=device)   # upstream gradient alone
         self.group, self.needs = group, needs
         self.in_dtypes, self.ls_shape = in_dtypes, ls_shape
         self.fwd_graph = self.bwd_graph = None
@@ -773,7 +801,7 @@ class _GraphEntry:
 
     def backward(self):
         global GRAPH_REPLAYED_LAUNCHES
-        run = lambda: _graph_backward(self.fwd_out, self.g, self.group, self.needs,  # noqa: E731
+        run = lambda: _graph_backward(self.fwd_out, self.g, self.g_ls, self.group, self.needs,  # noqa: E731
                                       self.in_dtypes, self.ls_shape)
         if self.bwd_graph is None and self.fwd_graph is not None:
             # (its inputs are the static outputs of the captured forward half)
@@ -855,7 +883,8 @@ class _FusedClipLossGraphed(torch.autograd.Function):
                 "fused CLIP loss (CUDA-graph mode): another forward of the same shape ran before this "
                 "backward and overwrote the saved statistics; set VLP_B200_CUDA_GRAPH=0 for such "
                 "schedules")
-        torch.mul(g_loss.detach().reshape(1).to(torch.float32), ctx.grad_scale, out=entry.g)
+        entry.g_ls.copy_(g_loss.detach().reshape(1).to(torch.float32))
+        torch.mul(entry.g_ls, ctx.grad_scale, out=entry.g)
         # gradients live in static buffers that the next backward of this shape overwrites
         d_i, d_t, d_ls = entry.backward()
         return (d_i if ctx.needs_input_grad[0] else None, d_t if ctx.needs_input_grad[1] else None,
@@ -875,6 +904,13 @@ def fused_clip_loss_from_embeddings(image_embeddings: torch.Tensor, text_embeddi
     process group for the sharded global-batch variant (each rank passes its local rows);
     ``grad_scale`` multiplies every gradient (use ``world_size`` under DDP gradient averaging).
     """
+    with _device_guard(image_embeddings, text_embeddings, logit_scale):
+        return _fused_clip_loss_from_embeddings(image_embeddings, text_embeddings, logit_scale, group,
+                                                grad_scale, _operands)
+
+
+def _fused_clip_loss_from_embeddings(image_embeddings, text_embeddings, logit_scale, group, grad_scale,
+                                     _operands):
     i_bf16 = t_bf16 = i_f16 = t_f16 = None
     if _operands is not None:
         i_bf16, t_bf16, i_f16, t_f16 = _operands
@@ -940,6 +976,11 @@ class _ProjectNormalize(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_emb, _g1, _g2):
+        with _device_guard(ctx.saved_tensors[0]):
+            return _ProjectNormalize._backward(ctx, d_emb)
+
+    @staticmethod
+    def _backward(ctx, d_emb):
         f32, w32, emb, inv_norm = ctx.saved_tensors
         if d_emb is None:
             return None, None
@@ -960,7 +1001,8 @@ class _ProjectNormalize(torch.autograd.Function):
 
 def project_normalize(features: torch.Tensor, projection: torch.Tensor):
     """(emb_fp32, emb_bf16, emb_f16) = normalize(features @ projection)."""
-    return _ProjectNormalize.apply(features, projection)
+    with _device_guard(features, projection):
+        return _ProjectNormalize.apply(features, projection)
 
 
 def fused_clip_loss(image_features: torch.Tensor, text_features: torch.Tensor,
@@ -982,6 +1024,11 @@ def fused_clip_loss(image_features: torch.Tensor, text_features: torch.Tensor,
 def clip_lse_stats(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor,
                    logit_scale_value: float):
     """Forward-only helper: (row_lse, col_lse, diag_logit) in natural-log units (no autograd)."""
+    with _device_guard(image_embeddings, text_embeddings):
+        return _clip_lse_stats(image_embeddings, text_embeddings, logit_scale_value)
+
+
+def _clip_lse_stats(image_embeddings, text_embeddings, logit_scale_value):
     s = min(math.exp(float(logit_scale_value)), LOGIT_SCALE_MAX)
     s = as_scale_tensor(s, image_embeddings.device)
     ib = image_embeddings.detach().to(torch.bfloat16).contiguous()

@@ -146,8 +146,10 @@ class ImageEncoder(nn.Module):
 
 
 class TextEncoder(nn.Module):
-    """DistilBERT / TinyBERT, CLS token (reference lines 38-60).  Pretrained weights are used when
-    they can be loaded; offline the same architecture is built from its config (random init)."""
+    """DistilBERT / TinyBERT, CLS token (reference lines 38-60).  Like the reference, construction
+    fails when the pretrained weights cannot be loaded; only an explicit VLP_B200_RANDOM_INIT=1
+    (benchmarks, tests: no network) builds the same architecture from its config with random
+    weights."""
 
     def __init__(self, text_encoder_model):
         super().__init__()
@@ -166,15 +168,13 @@ class TextEncoder(nn.Module):
     def _load(hub_name, kind):
         import os
         import transformers
-        offline = os.environ.get("HF_HUB_OFFLINE", "") == "1" or os.environ.get("VLP_B200_RANDOM_INIT") == "1"
-        if not offline:
-            try:
-                if kind == "distilbert":
-                    return transformers.DistilBertModel.from_pretrained(hub_name)
-                return transformers.AutoModel.from_pretrained(hub_name, torch_dtype="auto")
-            except Exception as exc:  # no network / no cache
-                logger.warning("TextEncoder: could not load %s (%s); building it from its config "
-                               "with random weights", hub_name, type(exc).__name__)
+        if os.environ.get("VLP_B200_RANDOM_INIT") != "1":
+            # (a failed download must not silently pre-train a random text tower: let it raise)
+            if kind == "distilbert":
+                return transformers.DistilBertModel.from_pretrained(hub_name)
+            return transformers.AutoModel.from_pretrained(hub_name, torch_dtype="auto")
+        logger.warning("TextEncoder: VLP_B200_RANDOM_INIT=1 -- building %s from its config with random weights",
+                       hub_name)
         if kind == "distilbert":
             return transformers.DistilBertModel(transformers.DistilBertConfig())
         cfg = transformers.BertConfig(hidden_size=312, num_hidden_layers=4, num_attention_heads=12,
@@ -356,10 +356,30 @@ class VisionLanguageModule(_LightningBase):
             raise TypeError("the fused head never materialises the N x N logits: pass the handle "
                             "returned by forward() (LogitsHandle) to _compute_loss")
         group, world = self._process_group()
+        if group is not None and not self._equal_shards(len(logits), group):
+            # the row-sharded loss needs the same number of pairs on every rank (a remainder batch
+            # of the reference's samplers may differ): this step falls back to the reference's own
+            # DDP semantics, the loss over the local pairs
+            group, world = None, 1
         loss, image_loss, text_loss = VF.fused_clip_loss_from_embeddings(
             logits.image_embeddings, logits.text_embeddings, logits.logit_scale, group=group,
             grad_scale=float(world), _operands=logits.operands)
         return loss, image_loss, text_loss
+
+    @staticmethod
+    def _equal_shards(n_loc: int, group) -> bool:
+        """True when every rank of ``group`` holds ``n_loc`` pairs (one tiny all-reduce per step)."""
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+            else torch.device("cpu")
+        t = torch.tensor([n_loc, -n_loc], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        hi, neg_lo = t.tolist()
+        if hi != -neg_lo:
+            logger.warning("fused CLIP loss: ranks hold between %d and %d pairs this step; using the "
+                           "local (per-rank) loss for it", -neg_lo, hi)
+            return False
+        return True
 
     # ------------------------------------------------------------------ retrieval metrics
     def precision_at_k_on_image_embeddings(self, image_embeddings, labels, ks: Sequence[int]) -> dict:
