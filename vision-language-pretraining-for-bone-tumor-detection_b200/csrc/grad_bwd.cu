@@ -892,7 +892,7 @@ static bool gb_layout(int n_rows, int n_cols, int d, GbLayout& L) {
   L.off_ring = o;
   o += (size_t)L.np * GB_RING_DEPTH * G_SLOT_BYTES;
   L.off_flags = o;
-  L.flag_bytes = ((size_t)L.np + 2 * (size_t)L.np * GB_RING_DEPTH + (size_t)nt) * GB_FLAG_STRIDE * 4;
+  L.flag_bytes = (3 * (size_t)L.np * GB_RING_DEPTH + (size_t)nt) * GB_FLAG_STRIDE * 4;
   o += align256(L.flag_bytes);
   L.total = o + 1024;
   return true;
@@ -1247,7 +1247,7 @@ int vlpclip_grad_both(const void* x, int ldx, const void* y, int ldy, const floa
   P.gring = base + L.off_ring;
   int* flags = (int*)(base + L.off_flags);
   P.ready = flags;
-  P.done_i = flags + (size_t)L.np * GB_FLAG_STRIDE;
+  P.done_i = flags + (size_t)L.np * GB_RING_DEPTH * GB_FLAG_STRIDE;
   P.done_t = P.done_i + (size_t)L.np * GB_RING_DEPTH * GB_FLAG_STRIDE;
   P.col_turn = P.done_t + (size_t)L.np * GB_RING_DEPTH * GB_FLAG_STRIDE;
   P.np = L.np;
