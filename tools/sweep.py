@@ -1,0 +1,69 @@
+"""BASELINE config 5: fused contrastive loss fwd+bwd over global batch x dim (x GPUs under torchrun).
+
+    python tools/sweep.py [--points 8192x512,32768x768,...] [--steps 10]
+    python -m torch.distributed.run --nproc-per-node G ... tools/sweep.py
+
+One JSON line per point on stdout (rank 0): ms/step (CUDA events, max over ranks), pairs/s, % of the
+measured dense bf16 peak on the 6 N^2 D convention.  Inputs: fp32 leaves with bf16-representable
+values (the parity surface), rho = 0.35, logit_scale = ln(1/0.07)."""
+import argparse, json, math, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.nn.functional as F
+import vlp_b200  # noqa
+from vlp_b200 import functional as VF
+import bench
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--points", default="8192x512,16384x512,32768x512,65536x512,8192x768,16384x768,32768x768,65536x768")
+ap.add_argument("--steps", type=int, default=10)
+args = ap.parse_args()
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
+group = None
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev); group = dist.group.WORLD
+peaks = bench.measured_peaks()
+for pt in args.points.split(","):
+    n, d = (int(v) for v in pt.split("x"))
+    b = n // world
+    g = torch.Generator(device=dev).manual_seed(42)
+    a = torch.randn(n, d, generator=g, device=dev); c = torch.randn(n, d, generator=g, device=dev)
+    c = 0.35 * a + math.sqrt(1 - 0.35 ** 2) * c
+    I = F.normalize(a).to(torch.bfloat16)[rank * b:(rank + 1) * b].float().contiguous()
+    T = F.normalize(c).to(torch.bfloat16)[rank * b:(rank + 1) * b].float().contiguous()
+    del a, c
+    ls = torch.tensor([bench.LOGIT_SCALE], device=dev, requires_grad=True)
+
+    def step():
+        Ii = I.detach().requires_grad_(True); Ti = T.detach().requires_grad_(True); ls.grad = None
+        loss, _, _ = VF.fused_clip_loss_from_embeddings(Ii, Ti, ls, group=group)
+        loss.backward()
+        return loss
+    for _ in range(4):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        loss = step()
+        if k % 2 == 1:
+            torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    if rank == 0:
+        tf = 6.0 * n * n * d / (ms * 1e-3) / 1e12 / world
+        print(json.dumps({"global_batch": n, "dim": d, "n_gpus": world, "ms_per_step": ms, "pairs_per_s": n / (ms * 1e-3),
+                          "algorithmic_tflops_per_gpu": tf, "pct_of_bf16_peak": 100 * tf / peaks["bf16_tflops"],
+                          "loss": float(loss.detach())}), flush=True)
+    VF.release_graphs()
+    torch.cuda.empty_cache()
+if world > 1:
+    dist.destroy_process_group()
