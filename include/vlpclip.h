@@ -212,6 +212,26 @@ int vlpclip_peer_open(const unsigned char* handle64, void** dev_ptr);
 int vlpclip_peer_close(void* dev_ptr);
 int vlpclip_peer_free(void* dev_ptr);
 
+/* ---- retrieval metrics without the M x M similarity matrix (VisionLanguageModule.py:364-439) ----
+ * Q [n_rows, d], K [n_cols, d]: L2-normalised embeddings as bf16 (row strides ldq / ldk elements).
+ * Both entry points run the forward sweep's tile mainloop (tcgen05, S tile in TMEM) with a ranking
+ * epilogue; similarities are never written to memory.  Order of two columns of a row: larger
+ * similarity first, equal similarities by ascending column index (a stable descending sort).
+ *   vlpclip_retrieval_ranks: rank[i] = number of columns ranked before column i in row i (needs
+ *     n_cols >= n_rows).  recall@k of recall_at_k_on_image_text_retreival (:402-439) is
+ *     mean(rank < k) for every k at once.
+ *   vlpclip_retrieval_topk: idx[i, 0..k) (and optionally val) = the k best columns of row i,
+ *     1 <= k <= 16; precision_at_k_on_image_embeddings (:364-400) takes k+1 of them, drops the
+ *     first and compares labels.
+ * workspace: vlpclip_retrieval_workspace_bytes(n_rows, n_cols, d, k) (k = 0 for the ranks). */
+size_t vlpclip_retrieval_workspace_bytes(int n_rows, int n_cols, int d, int k);
+int vlpclip_retrieval_ranks(const void* q_bf16, int ldq, const void* k_bf16, int ldk, int n_rows,
+                            int n_cols, int d, int* rank, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int vlpclip_retrieval_topk(const void* q_bf16, int ldq, const void* k_bf16, int ldk, int n_rows,
+                           int n_cols, int d, int k, int* idx, float* val, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- prologue: emb = normalize(feat @ W) (VisionLanguageModule.py:448-453) ----
  * feat [n, f] fp32, W [f, d] fp32 (x @ W convention, not nn.Linear).
  * emb_f32 [n, d] fp32 (returned to the caller), emb_bf16 / emb_f16 [n, d] (operands of the

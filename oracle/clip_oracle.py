@@ -242,6 +242,37 @@ def recall_at_k_on_image_text_retrieval(image_embeddings: torch.Tensor,
     return out
 
 
+def retrieval_ranks(queries: torch.Tensor, keys: torch.Tensor, chunk: int = 2048) -> torch.Tensor:
+    """rank[i] = number of keys ranked before key i for query i under (similarity desc, index asc),
+    i.e. the position of the paired key in a STABLE descending sort of row i of Q K^T.  With it
+    recall@k of reference :425-434 is mean(rank < k): `similarity_matrix.topk(k)` contains column i
+    iff fewer than k columns rank before it (exact ties excepted: topk leaves their order open).
+    fp64, evaluated in row chunks; works on any device."""
+    q, k = queries.double(), keys.double()
+    n = q.shape[0]
+    out = torch.empty(n, dtype=torch.int64, device=q.device)
+    cols = torch.arange(k.shape[0], device=q.device)
+    for lo in range(0, n, chunk):
+        sim = q[lo:lo + chunk] @ k.T
+        rows = torch.arange(lo, min(n, lo + chunk), device=q.device)
+        diag = sim[rows - lo, rows]
+        before = (sim > diag[:, None]) | ((sim == diag[:, None]) & (cols[None, :] < rows[:, None]))
+        out[lo:lo + chunk] = before.sum(dim=1)
+    return out
+
+
+def retrieval_topk(queries: torch.Tensor, keys: torch.Tensor, k: int, chunk: int = 2048) -> torch.Tensor:
+    """indices of the k best keys of every query under (similarity desc, index asc) -- the first k
+    entries of a stable descending sort of each row of Q K^T (reference :386-391 uses topk, which
+    agrees wherever the similarities are distinct).  fp64, row chunks, any device."""
+    q, kk = queries.double(), keys.double()
+    out = []
+    for lo in range(0, q.shape[0], chunk):
+        sim = q[lo:lo + chunk] @ kk.T
+        out.append(torch.sort(sim, dim=1, descending=True, stable=True).indices[:, :k])
+    return torch.cat(out)
+
+
 # --------------------------------------------------------------------------------------
 # seeded synthetic inputs (BASELINE.md section 3, SURVEY.md section 8d config 2)
 # --------------------------------------------------------------------------------------

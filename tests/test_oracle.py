@@ -148,3 +148,26 @@ def test_retrieval_oracle_perfect_alignment():
     labels = torch.arange(40) % 2
     p = O.precision_at_k_on_image_embeddings(e, labels, [3])
     assert 0.0 <= p[3] <= 1.0
+
+
+def test_rank_and_stable_topk_formulation_equals_the_reference_topk_metrics():
+    """The kernels compute ranks / a stable top-k (oracle.retrieval_ranks / retrieval_topk); on
+    tie-free data that is exactly the reference's topk-based recall@k and precision@k."""
+    g = torch.Generator().manual_seed(3)
+    img = torch.nn.functional.normalize(torch.randn(500, 48, generator=g))
+    txt = torch.nn.functional.normalize(img + 0.7 * torch.randn(500, 48, generator=g))
+    labels = torch.randint(0, 3, (500,), generator=g)
+    ks = [1, 3, 5, 10, 15]
+    rank = O.retrieval_ranks(img, txt)
+    ref_r = O.recall_at_k_on_image_text_retrieval(img, txt, ks)
+    for k in ks:
+        assert abs(int((rank < k).sum()) / 500 - ref_r[k]) < 1e-12
+    top = O.retrieval_topk(img, img, 16)
+    ref_p = O.precision_at_k_on_image_embeddings(img, labels, [3, 5, 10, 15])
+    hits = labels[:, None] == labels[top[:, 1:]]
+    for k in (3, 5, 10, 15):
+        assert abs((hits[:, :k].sum(dim=1).float() / k).mean().item() - ref_p[k]) < 1e-6
+    # ties: ascending index wins
+    q = torch.tensor([[1.0, 0.0]]); kk = torch.tensor([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    assert O.retrieval_topk(q, kk, 3)[0].tolist() == [0, 1, 2]
+    assert O.retrieval_ranks(torch.cat([q, q]), kk).tolist() == [0, 1]

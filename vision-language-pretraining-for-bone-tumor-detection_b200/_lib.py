@@ -59,6 +59,11 @@ _SIGNATURES = {
                                   c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vlpclip_grad_both_plan": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                        c_void_p, c_void_p, c_int, c_void_p]),
+    "vlpclip_retrieval_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "vlpclip_retrieval_ranks": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
+    "vlpclip_retrieval_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vlpclip_slot_sum": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p]),
     "vlpclip_peer_alloc": (c_int, [c_size_t, c_void_p, c_void_p]),
     "vlpclip_peer_open": (c_int, [c_void_p, c_void_p]),

@@ -37,6 +37,15 @@ constexpr uint32_t TMEM_X_COL = 0;      // bf16 X block: d/2 columns (256 at d =
 // S buffers of 128 columns sit at the top of TMEM: two (double buffered) while d <= 512, a single
 // one for 512 < d <= 768 (MMA and softmax of consecutive tiles then serialise)
 
+// what the softmax warps do with an S tile
+enum : int {
+  MODE_ROWS = 0,   // row (max, sum-exp) statistics
+  MODE_COLS = 1,   // + fused column statistics
+  MODE_RANK = 2,   // retrieval: how many columns beat the positive pair of each row (recall@k)
+  MODE_TOPK = 3    // retrieval: the RK best columns of each row, (value desc, index asc) (precision@k)
+};
+constexpr int RK = 16;   // entries per row of the streaming top-k (k_for_precision_at_k goes up to 15, + self)
+
 struct LseParams {
   int operand_f16;   // 0: X, Y are bf16; 1: fp16 (the backward's operand copies)
   const __nv_bfloat16* x;
@@ -56,6 +65,10 @@ struct LseParams {
   // sum_i exp2(k c_ij - ref) with a log2-domain reference `ref`; the positive pair is left out
   float* col_ref;       // [n_row_blocks][total_tiles * 128]
   float* col_l;         // [n_row_blocks][total_tiles * 128]
+  // retrieval modes: partial results per (chunk, column group), merged by rank_merge / topk_merge
+  int* part_cnt;        // MODE_RANK [n_chunks * FWD_CG][n_rows]
+  float* part_val;      // MODE_TOPK [n_chunks * FWD_CG][n_rows][RK]
+  int* part_idx;        // MODE_TOPK [n_chunks * FWD_CG][n_rows][RK]
 };
 
 struct FwdBarriers {
@@ -69,14 +82,25 @@ struct FwdBarriers {
   uint32_t pad_;
   float col_s[2][FWD_SMW][FWD_CPT];   // [tile parity][softmax warp][its column]: warp partial sums
   float col_r[2][FWD_SMW];            // their log2-domain references
+  float diag_s[128];                  // MODE_RANK: S_ii of the block's rows (from the diagonal tile)
 };
 
 constexpr float COL_HEADROOM = 100.f;  // partial sums carry 2^100: 226 log2 units of range below a
                                        // warp's largest row maximum before a term can underflow
 
-template <bool kCols>
+// (value desc, index asc): the order of a stable descending sort
+__device__ __forceinline__ bool rk_better(float s, int c, float v, int i) {
+  return s > v || (s == v && c < i);
+}
+
+template <int kMode>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p) {
+  constexpr bool kCols = kMode == MODE_COLS;
+  // MODE_RANK: every work item first sweeps the DIAGONAL tile of its row block (tile index = row
+  // block: the positive pair of row i is column i) to learn S_ii from the same MMAs that produce
+  // the values it is compared with -- duplicate captions then tie bit-exactly
+  constexpr int kLead = kMode == MODE_RANK ? 1 : 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -106,7 +130,8 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
   const uint32_t tmem = bars->tmem_base;
 
   const int n_items = p.n_row_blocks * p.n_chunks;
-  const float scale_log2 = __ldg(p.scale_ptr) * kLog2e;   // k = s * log2(e), device-side scalar
+  // k = s * log2(e), device-side scalar (the retrieval modes rank raw cosines: no temperature)
+  const float scale_log2 = kMode >= MODE_RANK ? 0.f : __ldg(p.scale_ptr) * kLog2e;
   const uint32_t nbuf = p.kblocks <= 8 ? 2u : 1u;
   const uint32_t tmem_s_col = 512u - nbuf * 128u;
 
@@ -117,7 +142,9 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       const int chunk = item / p.n_row_blocks;
       const int t0 = chunk * p.tiles_per_chunk;
       const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-      for (int t = t0; t < t1; ++t) {
+      const int rb_item = item % p.n_row_blocks;
+      for (int q = 0; q < kLead + t1 - t0; ++q) {
+        const int t = q < kLead ? rb_item : t0 + q - kLead;
         for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE, ++it) {
           const uint32_t st = it % FWD_STAGES;
           const uint32_t ph = (it / FWD_STAGES) & 1;
@@ -144,7 +171,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
       const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
       mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
       tc_fence_after();
-      for (int t = t0; t < t1; ++t, ++tile_ctr) {
+      for (int q = 0; q < kLead + t1 - t0; ++q, ++tile_ctr) {
         const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
         const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
         mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1);
@@ -227,9 +254,81 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         if (lane == 0) mbar_arrive(smem_u32(&bars->x_ready));
       }
 
-      float m_run = -INFINITY, mraw_run = -INFINITY, l_run = 0.f;
       // column holding this row's positive pair (none for padded rows)
       const int dcol = row_ok ? row - p.diag_shift : -1000000000;
+      if (kMode >= MODE_RANK) {
+        // ---- retrieval epilogues: ranks by the raw cosine, no exponentials ----
+        float diag = 0.f;
+        int cnt = 0;
+        float tv[RK];
+        int ti[RK];
+        if (kMode == MODE_TOPK) {
+#pragma unroll
+          for (int e = 0; e < RK; ++e) {
+            tv[e] = -INFINITY;
+            ti[e] = 0x7fffffff;
+          }
+        }
+        for (int q = 0; q < kLead + t1 - t0; ++q, ++tile_ctr) {
+          const int t = q < kLead ? rb : t0 + q - kLead;
+          const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+          const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+          mbar_wait(smem_u32(&bars->s_full[buf]), use & 1);
+          tc_fence_after();
+          uint32_t v[FWD_CPT];
+          tmem_ld_x32(tmem + lane_addr + tmem_s_col + buf * 128 + cg * FWD_CPT, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
+          const int col0 = t * 128 + cg * FWD_CPT;
+          if (kMode == MODE_RANK && q < kLead) {   // diagonal tile: publish S_ii to the row's 4 threads
+#pragma unroll
+            for (int j = 0; j < FWD_CPT; ++j)
+              if (col0 + j == dcol) bars->diag_s[row_in_blk] = __uint_as_float(v[j]);
+            bar_sync(2, FWD_SMW * 32);
+            diag = bars->diag_s[row_in_blk];
+            continue;
+          }
+#pragma unroll
+          for (int j = 0; j < FWD_CPT; ++j) {
+            const int c = col0 + j;
+            const float sv = c < p.n_cols ? __uint_as_float(v[j]) : -INFINITY;   // TMA zero-fill past n_cols
+            if (kMode == MODE_RANK) {
+              cnt += rk_better(sv, c, diag, dcol) ? 1 : 0;
+            } else if (rk_better(sv, c, tv[RK - 1], ti[RK - 1])) {
+              tv[RK - 1] = sv;
+              ti[RK - 1] = c;
+#pragma unroll
+              for (int e = RK - 1; e > 0; --e) {   // one bubble pass: the list was sorted
+                if (rk_better(tv[e], ti[e], tv[e - 1], ti[e - 1])) {
+                  const float fv = tv[e];
+                  tv[e] = tv[e - 1];
+                  tv[e - 1] = fv;
+                  const int fi = ti[e];
+                  ti[e] = ti[e - 1];
+                  ti[e - 1] = fi;
+                }
+              }
+            }
+          }
+        }
+        if (row_ok) {
+          const size_t o = (size_t)(chunk * FWD_CG + cg) * p.n_rows + row;
+          if (kMode == MODE_RANK) {
+            p.part_cnt[o] = cnt;
+          } else {
+#pragma unroll
+            for (int e = 0; e < RK; ++e) {
+              p.part_val[o * RK + e] = tv[e];
+              p.part_idx[o * RK + e] = ti[e];
+            }
+          }
+        }
+        if (kMode == MODE_RANK) bar_sync(2, FWD_SMW * 32);   // diag_s is rewritten by the next item
+        continue;
+      }
+      float m_run = -INFINITY, mraw_run = -INFINITY, l_run = 0.f;
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
         const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
@@ -447,6 +546,58 @@ col_merge_kernel(const float* __restrict__ col_ref, const float* __restrict__ co
   }
 }
 
+// retrieval: rank[i] = number of columns ranked before the positive pair of row i
+__global__ void rank_merge_kernel(const int* __restrict__ part_cnt, int nparts, int n, int* __restrict__ rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = 0;
+  for (int q = 0; q < nparts; ++q) c += part_cnt[(size_t)q * n + i];
+  rank[i] = c;
+}
+
+// retrieval: merge the partial top-RK lists of a row (each sorted) into its k best columns
+__global__ void topk_merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx,
+                                  int nparts, int n, int k, int* __restrict__ out_idx,
+                                  float* __restrict__ out_val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float tv[RK];
+  int ti[RK];
+#pragma unroll
+  for (int e = 0; e < RK; ++e) {
+    tv[e] = -INFINITY;
+    ti[e] = 0x7fffffff;
+  }
+  for (int q = 0; q < nparts; ++q) {
+    const float* pv = part_val + ((size_t)q * n + i) * RK;
+    const int* pi = part_idx + ((size_t)q * n + i) * RK;
+    for (int c = 0; c < RK; ++c) {
+      const float sv = pv[c];
+      const int sc = pi[c];
+      if (!rk_better(sv, sc, tv[RK - 1], ti[RK - 1])) break;   // the rest of this list ranks lower still
+      tv[RK - 1] = sv;
+      ti[RK - 1] = sc;
+#pragma unroll
+      for (int e = RK - 1; e > 0; --e) {
+        if (rk_better(tv[e], ti[e], tv[e - 1], ti[e - 1])) {
+          const float fv = tv[e];
+          tv[e] = tv[e - 1];
+          tv[e - 1] = fv;
+          const int fi = ti[e];
+          ti[e] = ti[e - 1];
+          ti[e - 1] = fi;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < RK; ++e)
+    if (e < k) {
+      out_idx[(size_t)i * k + e] = ti[e] == 0x7fffffff ? -1 : ti[e];
+      if (out_val) out_val[(size_t)i * k + e] = tv[e];
+    }
+}
+
 // out2[0] = sum(row_loss), out2[1] = sum(col_loss); single block, fixed order => reproducible
 __global__ void loss_reduce_kernel(const float* __restrict__ row_loss,
                                    const float* __restrict__ col_loss, int n,
@@ -636,14 +787,14 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   if (rc) return rc;
 
   const size_t smem = FWD_STAGES * FWD_STAGE_BYTES + sizeof(FwdBarriers) + 1024;
-  VLP_CUDA_OK(set_smem_attr_once((const void*)lse_partial_kernel<false>, (int)smem, 2));
-  VLP_CUDA_OK(set_smem_attr_once((const void*)lse_partial_kernel<true>, (int)smem, 3));
+  VLP_CUDA_OK(set_smem_attr_once((const void*)lse_partial_kernel<MODE_ROWS>, (int)smem, 2));
+  VLP_CUDA_OK(set_smem_attr_once((const void*)lse_partial_kernel<MODE_COLS>, (int)smem, 3));
   const int n_items = p.n_row_blocks * p.n_chunks;
   const int grid = n_items < nsm ? n_items : nsm;
   if (fused)
-    lse_partial_kernel<true><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+    lse_partial_kernel<MODE_COLS><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
   else
-    lse_partial_kernel<false><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+    lse_partial_kernel<MODE_ROWS><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   lse_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_m, p.part_l, nullptr, nparts,
@@ -658,6 +809,101 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
     VLP_CUDA_OK(cudaGetLastError());
   }
   return 0;
+}
+
+// ---- retrieval metrics without the M x M matrix (VisionLanguageModule.py:364-439) ----------------
+static size_t retrieval_ws_bytes(int n_rows, int n_cols, bool topk) {
+  const int n_row_blocks = (n_rows + 127) / 128, total_tiles = (n_cols + 127) / 128;
+  int nsm = usable_sms();
+  if (nsm <= 0) nsm = 148;
+  int n_chunks, tpc;
+  pick_chunks(n_row_blocks, total_tiles, nsm, &n_chunks, &tpc);
+  const size_t nparts = (size_t)n_chunks * FWD_CG;
+  return nparts * (size_t)n_rows * (topk ? (size_t)RK * 8 : 4) + 256;
+}
+
+size_t vlpclip_retrieval_workspace_bytes(int n_rows, int n_cols, int d, int k) {
+  (void)d;
+  if (n_rows <= 0 || n_cols <= 0) return 0;
+  return retrieval_ws_bytes(n_rows, n_cols, k > 0);
+}
+
+static int retrieval_impl(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols, int d,
+                          int k, int* out_rank, int* out_idx, float* out_val, void* workspace,
+                          size_t workspace_bytes, cudaStream_t stream) {
+  const bool topk = k > 0;
+  if (n_rows <= 0 || n_cols <= 0) return fail(-1, "retrieval: empty problem (%d x %d)", n_rows, n_cols);
+  if (!x || !y || !workspace || (topk ? !out_idx : !out_rank)) return fail(-1, "retrieval: null pointer");
+  if (topk && (k > RK || k > n_cols))
+    return fail(-1, "retrieval: k = %d unsupported (need 1 <= k <= min(%d, n_cols))", k, RK);
+  if (!topk && n_cols < n_rows)
+    return fail(-1, "retrieval: row i is paired with column i: need n_cols >= n_rows (%d < %d)", n_cols, n_rows);
+  if (d <= 0 || d % 8 != 0 || d > 768)
+    return fail(-1, "retrieval: embedding dim %d unsupported (need a multiple of 8, <= 768)", d);
+  if (ldx % 8 != 0 || ldy % 8 != 0) return fail(-1, "retrieval: row strides must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(-1, "retrieval: X must be 16-byte aligned");
+  int rc = check_device_sm100();
+  if (rc) return rc;
+  if (workspace_bytes < retrieval_ws_bytes(n_rows, n_cols, topk))
+    return fail(-1, "retrieval: workspace too small (%zu < %zu)", workspace_bytes,
+                retrieval_ws_bytes(n_rows, n_cols, topk));
+  LseParams p = {};
+  p.operand_f16 = 0;
+  p.x = (const __nv_bfloat16*)x;
+  p.ldx = ldx;
+  p.n_rows = n_rows;
+  p.n_cols = n_cols;
+  p.d = d;
+  p.kblocks = (d + 63) / 64;
+  p.total_tiles = (n_cols + 127) / 128;
+  p.n_row_blocks = (n_rows + 127) / 128;
+  const int nsm = usable_sms();
+  pick_chunks(p.n_row_blocks, p.total_tiles, nsm, &p.n_chunks, &p.tiles_per_chunk);
+  p.diag_shift = 0;
+  p.scale_ptr = nullptr;
+  const int nparts = p.n_chunks * FWD_CG;
+  if (topk) {
+    p.part_val = (float*)workspace;
+    p.part_idx = (int*)(p.part_val + (size_t)nparts * n_rows * RK);
+  } else {
+    p.part_cnt = (int*)workspace;
+  }
+  CUtensorMap map_y;
+  rc = make_tmap_sw128(&map_y, y, 2, (uint64_t)d, (uint64_t)n_cols, (uint64_t)ldy, 128);
+  if (rc) return rc;
+  const size_t smem = FWD_STAGES * FWD_STAGE_BYTES + sizeof(FwdBarriers) + 1024;
+  VLP_CUDA_OK(set_smem_attr_once((const void*)lse_partial_kernel<MODE_RANK>, (int)smem, 5));
+  VLP_CUDA_OK(set_smem_attr_once((const void*)lse_partial_kernel<MODE_TOPK>, (int)smem, 6));
+  const int n_items = p.n_row_blocks * p.n_chunks;
+  const int grid = n_items < nsm ? n_items : nsm;
+  if (topk) {
+    lse_partial_kernel<MODE_TOPK><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+    VLP_COUNT_LAUNCH(1);
+    topk_merge_kernel<<<(n_rows + 127) / 128, 128, 0, stream>>>(p.part_val, p.part_idx, nparts, n_rows, k,
+                                                                out_idx, out_val);
+  } else {
+    lse_partial_kernel<MODE_RANK><<<grid, FWD_THREADS, smem, stream>>>(map_y, p);
+    VLP_COUNT_LAUNCH(1);
+    rank_merge_kernel<<<(n_rows + 255) / 256, 256, 0, stream>>>(p.part_cnt, nparts, n_rows, out_rank);
+  }
+  VLP_COUNT_LAUNCH(1);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int vlpclip_retrieval_ranks(const void* q_bf16, int ldq, const void* k_bf16, int ldk, int n_rows,
+                            int n_cols, int d, int* rank, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  return retrieval_impl(q_bf16, ldq, k_bf16, ldk, n_rows, n_cols, d, 0, rank, nullptr, nullptr, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+int vlpclip_retrieval_topk(const void* q_bf16, int ldq, const void* k_bf16, int ldk, int n_rows,
+                           int n_cols, int d, int k, int* idx, float* val, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (k <= 0) return fail(-1, "retrieval_topk: k must be positive");
+  return retrieval_impl(q_bf16, ldq, k_bf16, ldk, n_rows, n_cols, d, k, nullptr, idx, val, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
 }
 
 int vlpclip_lse_fwd(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols, int d,
