@@ -301,6 +301,21 @@ def parity_check(torch, I_loc, T_loc, ls_value, rank, world, loss, dI_loc, dT_lo
                          "gradient on the global batch (max over ranks)"}
 
 
+def cpu_full_step(timeout_s=300):
+    """BASELINE.json configs[0]: the reference's ResNet34 + TinyBERT CLIP step (stock torch ops,
+    batch 32, synthetic 224 x 224 radiographs + 32-token captions) on THIS box's host cores, in the
+    same run (tools/full_step.py cpu, a subprocess so that its thread settings stay its own)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "full_step.py"), "cpu", "--batch", "32",
+                            "--dim", "128", "--steps", "2"], capture_output=True, text=True, timeout=timeout_s)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": (r.stderr or "no output")[-200:]}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"[:200]}
+
+
 def torch_gpu_baseline(torch, I, T, ls_value, steps=2):
     """Stock PyTorch on the same B200: the reference's own ops (fp32 GEMM, fp64 logits, two
     F.cross_entropy, autograd) on the whole batch -- the on-box bar SURVEY.md section 2 names."""
@@ -622,10 +637,12 @@ def run_ours(args):
             traffic = None
     cpu = None
     tgb = None
+    cfs = None
     if world == 1 and not args.skip_cpu:
         cpu = cpu_reference_sample(n, d, args.cpu_block, 2, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         tgb = torch_gpu_baseline(torch, sets[0][0], sets[0][1], LOGIT_SCALE)
+        cfs = cpu_full_step()
     n_weak = bw * world
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -664,6 +681,7 @@ def run_ours(args):
                                "note": "efficiency E(G) = this figure at G GPUs / the same figure at 1 GPU (SURVEY 8(d))"},
         "cpu_baseline": cpu,
         "torch_gpu_baseline": tgb,
+        "cpu_full_step": cfs,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps,

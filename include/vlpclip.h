@@ -49,6 +49,11 @@ unsigned long long vlpclip_launch_count(void);
 /* bf16 -> fp16 copy (values of unit-norm embeddings are exactly representable but for |x| < 2^-14) */
 int vlpclip_cast_bf16_to_f16(const void* src_bf16, void* dst_f16, size_t n_elems, void* stream);
 
+/* fp32 embeddings -> bf16 operand copy and (dst_f16 != NULL) the fp16 image of the bf16-rounded values,
+ * one pass (n_elems multiple of 4): the operands of the forward sweep / the backward GEMMs */
+int vlpclip_cast_f32_operands(const float* src_f32, void* dst_bf16, void* dst_f16, size_t n_elems,
+                              void* stream);
+
 /* ---- forward: per-row log-sum-exp statistics of  S = scale * X Y^T  ----
  * X: [n_rows, d] bf16 row-major (row stride ldx elements), Y: [n_cols, d] bf16 (row stride ldy).
  * The positive pair of row i is column i - diag_shift (if inside [0, n_cols)).

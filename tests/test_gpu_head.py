@@ -129,6 +129,11 @@ def test_module_training_step_end_to_end():
     m.on_train_epoch_start()
     loss = m.training_step(batch)
     assert torch.isfinite(loss)
+    # the epoch cache rows were written by the prologue kernel (bf16 operand copy), labels appended
+    ci, ct, cl = m._get_cached_embeddings_and_labels("train")
+    assert ci.dtype == torch.bfloat16 and ci.shape == (bsz, 128) and torch.equal(cl, batch["label"])
+    assert m.train_image_embeddings_and_labels_cached.img.data_ptr() == ci.data_ptr()
+    assert abs(ci.float().norm(dim=1) - 1).max() < 1e-2
     loss.backward()
     for name in ("image_projection", "text_projection", "logit_scale"):
         g = getattr(m, name).grad

@@ -191,3 +191,33 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["value"] > 0 and line["config"]["global_batch"] == 2048
+
+
+def test_epoch_cache_appends_without_reconcatenation():
+    """cache.EpochEmbeddingCache: reserve / commit semantics on CPU tensors (the buffers are plain
+    torch tensors; only the prologue kernel that fills the reserved rows needs a GPU)."""
+    from vlp_b200.cache import EpochEmbeddingCache
+    c = EpochEmbeddingCache(initial_rows=4)
+    with pytest.raises(ValueError):
+        c.get()
+    g = torch.Generator().manual_seed(0)
+    chunks = [(torch.randn(n, 8, generator=g), torch.randn(n, 8, generator=g), torch.arange(n)) for n in (3, 5, 2)]
+    # step 1: rows written "by the kernel" into the reserved views
+    iv, tv = c.reserve(3, 8, "cpu")
+    iv.copy_(chunks[0][0]); tv.copy_(chunks[0][1])
+    c.commit(chunks[0][0], chunks[0][1], chunks[0][2], written=True)
+    ptr = c.img.data_ptr()
+    # step 2 outgrows the buffer (4 rows): it doubles and keeps the rows; plain copy path
+    c.commit(chunks[1][0], chunks[1][1], chunks[1][2])
+    assert c.img.shape[0] == 8 and c.img.data_ptr() != ptr
+    # a reserve whose rows are NOT the ones committed falls back to the copy
+    c.reserve(7, 8, "cpu")
+    c.commit(chunks[2][0], chunks[2][1], chunks[2][2], written=True)
+    i, t, l = c.get()
+    assert len(c) == 10 and i.dtype == torch.bfloat16
+    assert torch.equal(i.float(), torch.cat([x[0] for x in chunks]).to(torch.bfloat16).float())
+    assert torch.equal(t.float(), torch.cat([x[1] for x in chunks]).to(torch.bfloat16).float())
+    assert torch.equal(l, torch.cat([x[2] for x in chunks]))
+    assert "label" in c and torch.equal(c["label"], l)
+    c.reset()
+    assert len(c) == 0 and c.img.shape[0] == 16      # buffers are kept across epochs

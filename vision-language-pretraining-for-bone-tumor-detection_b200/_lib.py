@@ -20,6 +20,7 @@ _SIGNATURES = {
     "vlpclip_launch_count": (ctypes.c_ulonglong, []),
     "vlpclip_set_sm_limit": (c_int, [c_int]),
     "vlpclip_cast_bf16_to_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlpclip_cast_f32_operands": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vlpclip_lse_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlpclip_lse_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -667,6 +667,29 @@ __global__ void cast_bf16_to_f16_kernel(const __nv_bfloat16* __restrict__ src,
   for (; i < n; i += stride) dst[i] = __float2half_rn(__bfloat162float(src[i]));
 }
 
+// fp32 embeddings -> both operand copies in one pass: bf16 (forward sweep) and the fp16 image of the
+// bf16-ROUNDED value (backward GEMMs: the recompute must see exactly the forward's operands)
+__global__ void cast_f32_operands_kernel(const float4* __restrict__ src, uint2* __restrict__ dst_bf16,
+                                         uint2* __restrict__ dst_f16, size_t n4) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = src[i];
+    const __nv_bfloat162 b0 = __floats2bfloat162_rn(v.x, v.y), b1 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 ob;
+    ob.x = *reinterpret_cast<const uint32_t*>(&b0);
+    ob.y = *reinterpret_cast<const uint32_t*>(&b1);
+    dst_bf16[i] = ob;
+    if (dst_f16) {
+      const __half2 h0 = __floats2half2_rn(__low2float(b0), __high2float(b0));
+      const __half2 h1 = __floats2half2_rn(__low2float(b1), __high2float(b1));
+      uint2 oh;
+      oh.x = *reinterpret_cast<const uint32_t*>(&h0);
+      oh.y = *reinterpret_cast<const uint32_t*>(&h1);
+      dst_f16[i] = oh;
+    }
+  }
+}
+
 // ---- chunking policy: items = row_blocks * chunks should fill whole waves of SMs ----
 static void pick_chunks(int n_row_blocks, int total_tiles, int n_sm, int* n_chunks,
                         int* tiles_per_chunk) {
@@ -724,6 +747,22 @@ int vlpclip_cast_bf16_to_f16(const void* src, void* dst, size_t n, void* stream)
   if (blocks > 148 * 8) blocks = 148 * 8;
   cast_bf16_to_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)src, (__half*)dst, n);
+  VLP_COUNT_LAUNCH(1);
+  VLP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int vlpclip_cast_f32_operands(const float* src, void* dst_bf16, void* dst_f16, size_t n, void* stream) {
+  if (n == 0) return 0;
+  if (!src || !dst_bf16) return fail(-1, "cast_f32_operands: null pointer");
+  if (n % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(dst_bf16) & 7) != 0 || (reinterpret_cast<uintptr_t>(dst_f16) & 7) != 0)
+    return fail(-1, "cast_f32_operands: need n %% 4 == 0 and 16-byte aligned source (8-byte aligned outputs)");
+  const size_t n4 = n / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cast_f32_operands_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)src, (uint2*)dst_bf16,
+                                                                     (uint2*)dst_f16, n4);
   VLP_COUNT_LAUNCH(1);
   VLP_CUDA_OK(cudaGetLastError());
   return 0;

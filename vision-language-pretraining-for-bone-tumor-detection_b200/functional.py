@@ -118,6 +118,19 @@ def cast_bf16_to_f16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def cast_f32_operands(src: torch.Tensor, want_f16: bool = True):
+    """(bf16, fp16 | None) operand copies of fp32 embeddings in one pass (the fp16 copy is the image
+    of the bf16-rounded values, so forward and backward see identical operands)."""
+    _require_cuda(src, "src")
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.numel() % 4 == 0
+    b = torch.empty_like(src, dtype=torch.bfloat16)
+    h = torch.empty_like(src, dtype=torch.float16) if want_f16 else None
+    lib = _lib.load()
+    _lib.check(lib.vlpclip_cast_f32_operands(src.data_ptr(), b.data_ptr(), h.data_ptr() if want_f16 else None,
+                                             src.numel(), _stream()), "cast_f32_operands")
+    return b, h
+
+
 def lse_stats(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shift: int = 0):
     """Row statistics of ``scale * x @ y.T``: (row_max [n], row_l [n], diag [n]).
 
@@ -606,10 +619,20 @@ class _FusedClipLoss(torch.autograd.Function):
         # (d/dl clamp(e^l, max=100) = e^l if e^l <= 100 else 0)
         scale, dscale_dls = scale_from_logit_scale(logit_scale)
 
-        if i_bf16 is None:
-            i_bf16 = image_embeddings.detach().to(torch.bfloat16).contiguous()
-        if t_bf16 is None:
-            t_bf16 = text_embeddings.detach().to(torch.bfloat16).contiguous()
+        # operand copies: fp32 embeddings take one fused pass (bf16 + fp16 together, single GPU)
+        needs_grad_any = any(ctx.needs_input_grad[:3])
+        single = sharded.group_info(group)[0] == 1
+
+        def _operands(e, b16, f16):
+            if b16 is None:
+                if e.dtype == torch.float32 and single and e.numel() % 4 == 0:
+                    b16, f16_new = cast_f32_operands(e.detach().contiguous(), want_f16=needs_grad_any and f16 is None)
+                    f16 = f16 if f16 is not None else f16_new
+                else:
+                    b16 = e.detach().to(torch.bfloat16).contiguous()
+            return b16, f16
+        i_bf16, i_f16 = _operands(image_embeddings, i_bf16, i_f16)
+        t_bf16, t_f16 = _operands(text_embeddings, t_bf16, t_f16)
 
         # fp16 operand copies for the backward: produced on a side stream so that the two small
         # casts run underneath the forward sweep instead of in front of the backward
@@ -946,7 +969,7 @@ class _ProjectNormalize(torch.autograd.Function):
     """emb = F.normalize(features @ W)  (reference :448-449, :452-453)."""
 
     @staticmethod
-    def forward(ctx, features, weight):
+    def forward(ctx, features, weight, out_bf16=None):
         _require_cuda(features, "features")
         _require_cuda(weight, "projection")
         if features.dim() != 2 or weight.dim() != 2 or features.shape[1] != weight.shape[0]:
@@ -959,7 +982,14 @@ class _ProjectNormalize(torch.autograd.Function):
         lib = _lib.load()
         dev = f32.device
         emb = torch.empty(n, d, dtype=torch.float32, device=dev)
-        emb_bf16 = torch.empty(n, d, dtype=torch.bfloat16, device=dev)
+        if out_bf16 is None:
+            emb_bf16 = torch.empty(n, d, dtype=torch.bfloat16, device=dev)
+        else:   # caller-provided destination of the bf16 operand copy (rows of the epoch cache)
+            if (out_bf16.dtype != torch.bfloat16 or tuple(out_bf16.shape) != (n, d) or not out_bf16.is_contiguous()
+                    or out_bf16.device != dev or out_bf16.data_ptr() % 16 != 0):
+                raise ValueError("out_bf16 must be a contiguous, 16-byte aligned bf16 [batch, dim] tensor on the "
+                                 "features' device")
+            emb_bf16 = out_bf16
         emb_f16 = torch.empty(n, d, dtype=torch.float16, device=dev)
         inv_norm = torch.empty(n, dtype=torch.float32, device=dev)
         nbytes = lib.vlpclip_project_workspace_bytes(n, f, d)
@@ -983,7 +1013,7 @@ class _ProjectNormalize(torch.autograd.Function):
     def _backward(ctx, d_emb):
         f32, w32, emb, inv_norm = ctx.saved_tensors
         if d_emb is None:
-            return None, None
+            return None, None, None
         n, f = f32.shape
         d = w32.shape[1]
         lib = _lib.load()
@@ -996,13 +1026,14 @@ class _ProjectNormalize(torch.autograd.Function):
             d_feat = _gemm_tf32(du, w32, n, f, d, 0, 1).to(ctx.in_dtypes[0])      # du @ W^T
         if ctx.needs_input_grad[1]:
             d_w = _gemm_tf32(f32, du, f, d, n, 1, 0).to(ctx.in_dtypes[1])          # feat^T @ du
-        return d_feat, d_w
+        return d_feat, d_w, None
 
 
-def project_normalize(features: torch.Tensor, projection: torch.Tensor):
-    """(emb_fp32, emb_bf16, emb_f16) = normalize(features @ projection)."""
+def project_normalize(features: torch.Tensor, projection: torch.Tensor, out_bf16: Optional[torch.Tensor] = None):
+    """(emb_fp32, emb_bf16, emb_f16) = normalize(features @ projection).  ``out_bf16``: optional
+    destination of the bf16 copy (e.g. rows of ``cache.EpochEmbeddingCache``), written by the kernel."""
     with _device_guard(features, projection):
-        return _ProjectNormalize.apply(features, projection)
+        return _ProjectNormalize.apply(features, projection, out_bf16)
 
 
 def fused_clip_loss(image_features: torch.Tensor, text_features: torch.Tensor,

@@ -31,6 +31,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as VF
+from .cache import EpochEmbeddingCache
 
 logger = logging.getLogger("project")
 
@@ -272,8 +273,10 @@ class VisionLanguageModule(_LightningBase):
             dm, _ = next(self.downstream_datamodule.get_cv_splits())
             self.downstream_train_dataloader = dm.train_dataloader()
             self.downstream_val_dataloaders = dm.val_dataloader()
-        self.train_image_embeddings_and_labels_cached = {}
-        self.val_image_embeddings_and_labels_cached = {}
+        # epoch caches: preallocated bf16 buffers the prologue kernel writes into (cache.py)
+        self.train_image_embeddings_and_labels_cached = EpochEmbeddingCache()
+        self.val_image_embeddings_and_labels_cached = EpochEmbeddingCache()
+        self._cache_pending = None
         logger.info("VisionLanguageModule (fused B200 head): initialised with %s", dict(self.hparams))
 
     # ------------------------------------------------------------------ optimiser (lines 130-297)
@@ -339,9 +342,15 @@ class VisionLanguageModule(_LightningBase):
     def forward(self, batch):
         image_features = self.image_encoder(batch["x-ray"])
         text_features = self.text_encoder(**batch["caption_tokenized"])
-        # projection + L2-normalise (reference :448-453) on the fused tf32 kernel
-        i_emb, i_bf16, i_f16 = VF.project_normalize(image_features, self.image_projection)
-        t_emb, t_bf16, t_f16 = VF.project_normalize(text_features, self.text_projection)
+        # projection + L2-normalise (reference :448-453) on the fused tf32 kernel; its bf16 operand
+        # copy of the embeddings lands directly in the next rows of the epoch cache
+        cache = (self.train_image_embeddings_and_labels_cached if self.training
+                 else self.val_image_embeddings_and_labels_cached)
+        i_view, t_view = cache.reserve(image_features.shape[0], self.image_projection.shape[1],
+                                       image_features.device)
+        i_emb, i_bf16, i_f16 = VF.project_normalize(image_features, self.image_projection, out_bf16=i_view)
+        t_emb, t_bf16, t_f16 = VF.project_normalize(text_features, self.text_projection, out_bf16=t_view)
+        self._cache_pending = (cache, i_emb, t_emb)
         handle = LogitsHandle(i_emb, t_emb, self.logit_scale, (i_bf16, t_bf16, i_f16, t_f16))
         return handle, i_emb, t_emb
 
@@ -415,24 +424,25 @@ class VisionLanguageModule(_LightningBase):
         assert mode in ["train", "val"], f"Invalid mode: {mode}"
         cache = (self.train_image_embeddings_and_labels_cached if mode == "train"
                  else self.val_image_embeddings_and_labels_cached)
-        # chunks are kept detached and concatenated once on read (the reference re-concatenates the
-        # whole cache, autograd graph attached, on every step)
-        cache.setdefault("image_embedding", []).append(image_embeddings.detach())
-        cache.setdefault("text_embedding", []).append(text_embeddings.detach())
-        cache.setdefault("label", []).append(labels.detach())
+        # the embeddings forward() just produced already sit in the cache rows it reserved (written
+        # by the prologue kernel); anything else is copied in (detached: no autograd graph is kept)
+        pend = self._cache_pending
+        written = (pend is not None and pend[0] is cache and pend[1] is image_embeddings
+                   and pend[2] is text_embeddings)
+        cache.commit(image_embeddings, text_embeddings, labels, written=written)
+        self._cache_pending = None
 
     def _get_cached_embeddings_and_labels(self, mode):
         assert mode in ["train", "val"], f"Invalid mode: {mode}"
         cache = (self.train_image_embeddings_and_labels_cached if mode == "train"
                  else self.val_image_embeddings_and_labels_cached)
-        if "image_embedding" not in cache or "label" not in cache:
+        if len(cache) == 0:
             raise ValueError(f"No cached embeddings and labels for mode: {mode}")
-        return (torch.cat(cache["image_embedding"]), torch.cat(cache["text_embedding"]),
-                torch.cat(cache["label"]))
+        return cache.get()      # views of the bf16 buffers: no concatenation
 
     # ------------------------------------------------------------------ Lightning hooks (631-705)
     def on_train_epoch_start(self):
-        self.train_image_embeddings_and_labels_cached = {}
+        self.train_image_embeddings_and_labels_cached.reset()
 
     def training_step(self, batch, batch_idx=None):
         logits, image_embeddings, text_embeddings = self(batch)
@@ -453,7 +463,7 @@ class VisionLanguageModule(_LightningBase):
 
     def on_validation_epoch_start(self):
         self.val_combined_loss.reset()
-        self.val_image_embeddings_and_labels_cached = {}
+        self.val_image_embeddings_and_labels_cached.reset()
 
     def validation_step(self, batch, batch_idx, dataloader_idx=0):
         logits, image_embeddings, text_embeddings = self(batch)
