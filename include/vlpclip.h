@@ -200,6 +200,28 @@ int vlpclip_grad_both(const void* x_f16, int ldx, const void* y_f16, int ldy, co
                       int dx_bf16, void* dx, int dy_bf16, void* dy, void* const* dy_owner_rows,
                       int n_owners, int rows_per_owner, float* dscale, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* ---- duplicate-caption-aware (masked) InfoNCE: SURVEY section 8 (f3) ----
+ * row_ids [n_rows] / col_ids [n_cols]: int32 caption ids >= 0 (device).  A logit whose row and column
+ * carry the same id is NOT a negative: unless it is the positive pair itself it is excluded from both
+ * soft-max denominators (forward) and gets G = 0 (backward).  The mask is the one of the reference's
+ * _get_mask (VisionLanguageModule.py:506-530: 0 where captions agree off the diagonal); the
+ * reference's own use of it is deprecated code (:535-547), so "excluded" is this library's definition.
+ * The forward entry is vlpclip_lse_fwd_fused(_f16) plus the ids (operand_f16 selects the operand type);
+ * the backward entry is vlpclip_grad_both plus the ids, fed with the masked statistics. */
+int vlpclip_lse_fwd_fused_masked(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,
+                                 int d, int operand_f16, const float* scale, int diag_shift,
+                                 const int* row_ids, const int* col_ids, float* row_max, float* row_l,
+                                 float* diag, float* col_max, float* col_l, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+int vlpclip_grad_both_masked(const void* x_f16, int ldx, const void* y_f16, int ldy, const float* x_max,
+                             const float* x_lg2l, const float* x_q, const float* y_max,
+                             const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
+                             const float* scale, int diag_shift, int n_global, float w_row, float w_col,
+                             const float* out_mul, int dx_bf16, void* dx, int dy_bf16, void* dy,
+                             void* const* dy_owner_rows, int n_owners, int rows_per_owner, float* dscale,
+                             const int* row_ids, const int* col_ids, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* host-only: the schedule of vlpclip_grad_both for np producer slots and nq >= np dT consumers
  * (np <= 0: the split used on the current device).  info[8] = {phases, nominal steps, dI partial
  * slots, runs, waves, np, nq, 0}; prod rows = {slot, step, row block, column tile, dI partial slot

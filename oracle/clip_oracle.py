@@ -208,6 +208,41 @@ def sharded_closed_form(I: np.ndarray, T: np.ndarray, logit_scale: float, world:
 
 
 # --------------------------------------------------------------------------------------
+# duplicate-caption mask (reference lines 506-530) -- "next" row f3
+# --------------------------------------------------------------------------------------
+def reference_get_mask(caption_ids: torch.Tensor) -> torch.Tensor:
+    """VisionLanguageModule._get_mask, lines 506-530, on caption ids instead of strings (the
+    reference maps the strings to ids first, :520-521): 0.0 where two DIFFERENT samples carry the
+    same caption, 1.0 elsewhere."""
+    eq = caption_ids.unsqueeze(0) == caption_ids.unsqueeze(1)                    # :524
+    mask = torch.ones_like(eq, dtype=torch.float)                               # :527
+    mask[eq & ~torch.eye(len(caption_ids), dtype=torch.bool, device=eq.device)] = 0.0   # :528
+    return mask
+
+
+def masked_loss_and_grads_from_embeddings(I: torch.Tensor, T: torch.Tensor, logit_scale: torch.Tensor,
+                                          caption_ids: torch.Tensor, dtype=torch.float64) -> Dict[str, torch.Tensor]:
+    """Symmetric cross-entropy of lines 456-459 + 550-552 with the masked entries of
+    ``reference_get_mask`` EXCLUDED from both soft-maxes (logit -> -inf), and its autograd gradients.
+    The reference's own application of the mask sits behind a DeprecationWarning (:541-544) and is
+    not in the source any more; "duplicates are not negatives" is the definition the kernels
+    implement (vlpclip_lse_fwd_fused_masked / vlpclip_grad_both_masked)."""
+    I = I.detach().to(dtype).clone().requires_grad_(True)
+    T = T.detach().to(dtype).clone().requires_grad_(True)
+    ls = logit_scale.detach().to(dtype).clone().requires_grad_(True)
+    scale = torch.clamp(ls.exp(), max=LOGIT_SCALE_MAX)                          # :456-457
+    logits = (I @ T.T) * scale                                                  # :459
+    logits = logits.masked_fill(reference_get_mask(caption_ids) == 0, float("-inf"))
+    labels = torch.arange(len(logits))                                          # :533
+    image_loss = F.cross_entropy(logits, labels)                                # :550
+    text_loss = F.cross_entropy(logits.T, labels)                               # :551
+    loss = (image_loss + text_loss) / 2                                         # :552
+    loss.backward()
+    return {"loss": loss.detach(), "image_loss": image_loss.detach(), "text_loss": text_loss.detach(),
+            "dI": I.grad, "dT": T.grad, "dlogit_scale": ls.grad}
+
+
+# --------------------------------------------------------------------------------------
 # retrieval metrics (reference lines 364-439) -- "next" row f1
 # --------------------------------------------------------------------------------------
 def precision_at_k_on_image_embeddings(image_embeddings: torch.Tensor, labels: torch.Tensor,

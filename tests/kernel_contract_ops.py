@@ -23,7 +23,34 @@ class ContractOps:
         return row_max, e.sum(dim=1), diag
 
     @staticmethod
-    def lse_stats_fused(x, y, scale, diag_shift):
+    def _dup_mask(row_ids, col_ids, n_rows, n_cols, diag_shift):
+        """True where row and column carry the same caption id off the positive pair."""
+        m = row_ids.reshape(-1, 1) == col_ids.reshape(1, -1)
+        rows = torch.arange(n_rows)
+        dcol = rows - diag_shift
+        has = (dcol >= 0) & (dcol < n_cols)
+        m[rows[has], dcol[has]] = False
+        return m
+
+    @staticmethod
+    def lse_stats_fused(x, y, scale, diag_shift, row_ids=None, col_ids=None):
+        if row_ids is not None:
+            c = x.double() @ y.double().T
+            n_rows, n_cols = c.shape
+            mask = ContractOps._dup_mask(row_ids, col_ids, n_rows, n_cols, diag_shift)
+            rows = torch.arange(n_rows)
+            dcol = rows - diag_shift
+            has = (dcol >= 0) & (dcol < n_cols)
+            diag = torch.zeros(n_rows, dtype=torch.float64)
+            diag[has] = c[rows[has], dcol[has]]
+            cm = c.masked_fill(mask, float("-inf"))
+            row_max = cm.max(dim=1).values
+            e = torch.exp(scale * (cm - row_max[:, None]))
+            e[rows[has], dcol[has]] = 0.0
+            col_ref = cm.max(dim=0).values + 0.25
+            ec = torch.exp(scale * (cm - col_ref[None, :]))
+            ec[rows[has], dcol[has]] = 0.0
+            return row_max, e.sum(dim=1), diag, col_ref, ec.sum(dim=0)
         row_max, row_l, diag = ContractOps.lse_stats(x, y, scale, diag_shift)
         c = x.double() @ y.double().T
         n_rows, n_cols = c.shape
@@ -54,7 +81,7 @@ class ContractOps:
 
     @staticmethod
     def grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
-             out_mul=None, out_dtype=None):
+             out_mul=None, out_dtype=None, row_ids=None, col_ids=None):
         x = x.double(); y = y.double()
         xm, xlg, xq = x_stats
         ym, ylg, yq = y_stats
@@ -67,6 +94,8 @@ class ContractOps:
         rows = torch.arange(n_rows)
         dcol = rows - diag_shift
         has = (dcol >= 0) & (dcol < n_cols)
+        if row_ids is not None:
+            g[ContractOps._dup_mask(row_ids, col_ids, n_rows, n_cols, diag_shift)] = 0.0
         g[rows[has], dcol[has]] = -(w_row * xq[rows[has]] + w_col * yq[dcol[has]])
         g = g / (2.0 * n_global)
         dx = scale * (g @ y)
@@ -77,13 +106,13 @@ class ContractOps:
 
     @staticmethod
     def grad_both(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
-                  out_mul=None, out_dtypes=None, window=None):
+                  out_mul=None, out_dtypes=None, window=None, row_ids=None, col_ids=None):
         """Contract of vlpclip_grad_both: (dX, dY, dscale) of ONE sweep; dY = G^T X is the other
         direction's dX with the roles of X and Y (and of the weights) swapped."""
         dx, ds = ContractOps.grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
-                                  want_dscale, out_mul)
+                                  want_dscale, out_mul, None, row_ids, col_ids)
         dy, _ = ContractOps.grad(y, x, y_stats, x_stats, scale, -diag_shift, n_global, w_col, w_row,
-                                 False, out_mul)
+                                 False, out_mul, None, col_ids, row_ids)
         return dx, dy, ds
 
     @staticmethod
@@ -142,15 +171,16 @@ class WindowContractOps(ContractOps):
 
     @classmethod
     def grad_both(cls, x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
-                  out_mul=None, out_dtypes=None, window=None):
+                  out_mul=None, out_dtypes=None, window=None, row_ids=None, col_ids=None):
         import torch.distributed as dist
         if window is None:
             return ContractOps.grad_both(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row,
-                                         w_col, want_dscale, out_mul)
+                                         w_col, want_dscale, out_mul, None, None, row_ids, col_ids)
         dx, ds = ContractOps.grad(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
-                                  want_dscale, out_mul)
+                                  want_dscale, out_mul, None, row_ids, col_ids)
         # the dY rows leave unscaled through the owners' slots (out_mul is applied by scatter_finish)
-        dy, _ = ContractOps.grad(y, x, y_stats, x_stats, scale, -diag_shift, n_global, w_col, w_row, False)
+        dy, _ = ContractOps.grad(y, x, y_stats, x_stats, scale, -diag_shift, n_global, w_col, w_row, False,
+                                 None, None, col_ids, row_ids)
         window.parity ^= 1
         parts = [torch.empty_like(dy) for _ in range(window.world)]
         dist.all_gather(parts, dy.contiguous(), group=window.group)

@@ -127,3 +127,56 @@ def test_single_process_plan_matches_oracle():
                                              single_sweep=single_sweep)
         assert O.rel_err(d_i.numpy(), ref["dI"]) < 1e-12 and O.rel_err(d_t.numpy(), ref["dT"]) < 1e-12
         assert abs(float(ds[0]) - ref["dscale"]) < 1e-12
+
+
+def _masked_worker(rank, world, port, n, d, ls, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import vlp_b200  # noqa: F401
+        from vlp_b200 import sharded
+        from kernel_contract_ops import WindowContractOps
+        from oracle import clip_oracle as O
+        I, T = O.make_embeddings(n, d, rho=0.35, seed=42)
+        ids = torch.arange(n) % 7          # 7 distinct captions: many duplicates in every shard
+        b = n // world
+        sl = slice(rank * b, (rank + 1) * b)
+        scale = min(math.exp(ls), 100.0)
+        plan = sharded.forward_plan(WindowContractOps, I[sl].double(), T[sl].double(), scale, dist.group.WORLD,
+                                    ids_loc=ids[sl])
+        d_i, d_t, ds = sharded.backward_plan(WindowContractOps, I[sl].double(), plan["t_all"], plan["r_stats"],
+                                             plan["c_stats"], scale, b, n, rank, world, dist.group.WORLD,
+                                             tail_barrier=True, ids=plan["ids"])
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=plan["loss"].numpy(), dI=d_i.numpy(),
+                 dT=d_t.numpy(), ds=ds.numpy())
+    finally:
+        try:
+            from kernel_contract_ops import WindowContractOps as _W
+            _W.windows.clear()
+        except Exception:
+            pass
+        import gc
+        gc.collect()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,d,ls", [(2, 56, 16, 2.6593), (4, 64, 16, 3.5)])
+def test_sharded_plan_with_duplicate_caption_mask_matches_oracle(tmp_path, world, n, d, ls):
+    """The caption ids of the local rows are all-gathered for the columns; masked statistics and the
+    masked single-sweep backward reproduce the oracle's masked loss and gradients on the global batch."""
+    from oracle import clip_oracle as O
+    mp.spawn(_masked_worker, args=(world, _free_port(), n, d, ls, str(tmp_path)), nprocs=world, join=True)
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=42)
+    ref = O.masked_loss_and_grads_from_embeddings(I, T, torch.tensor([ls], dtype=torch.float64), torch.arange(n) % 7)
+    s = min(math.exp(ls), 100.0)
+    b = n // world
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        assert abs(float(got["loss"]) - float(ref["loss"])) < 1e-10
+        assert O.rel_err(got["dI"], ref["dI"][r * b:(r + 1) * b].numpy()) < 1e-10
+        assert O.rel_err(got["dT"], ref["dT"][r * b:(r + 1) * b].numpy()) < 1e-10
+        ref_ds = float(ref["dlogit_scale"]) / s if math.exp(ls) <= 100 else 0.0
+        assert abs(float(got["ds"][0]) - ref_ds) < 1e-10 * max(1.0, abs(ref_ds))

@@ -149,6 +149,14 @@ def test_module_training_step_end_to_end():
         ref = O.closed_form(ie.to(torch.bfloat16).float().cpu().numpy(), te.to(torch.bfloat16).float().cpu().numpy(),
                             float(m.logit_scale.detach()))
         assert abs(l2.item() - ref["loss"]) < 1e-4 * ref["loss"]
+    # opt-in duplicate-caption mask: all 24 captions are "c" here, so every pair but the positives is
+    # masked and the loss is exactly 0 (each row / column only sees its positive pair)
+    m.mask_duplicate_captions = True
+    with torch.no_grad():
+        handle, _, _ = m(batch)
+        l3, _, _ = m._compute_loss(handle, False, False, batch["caption"])
+    assert abs(l3.item()) < 1e-6
+    m.mask_duplicate_captions = False
     m.on_train_epoch_end()
     m.on_validation_epoch_start()
     m.validation_step(batch, 0, dataloader_idx=0)

@@ -195,6 +195,36 @@ def test_single_sweep_backward_bf16_outputs_and_upstream_gradient(VF):
     assert rel(dIh, 0.37 * dI) < 4e-3 and rel(dTh, 0.37 * dT) < 4e-3      # bf16 rounding of the outputs
 
 
+@pytest.mark.parametrize("n,d,n_captions,ls", [(300, 64, 40, 2.6593), (1000, 128, 88, 3.0), (4096, 512, 880, 2.6593),
+                                               (129, 72, 5, math.log(50.0))])
+def test_duplicate_caption_mask_matches_oracle(VF, n, d, n_captions, ls):
+    """f3: pairs (i, j != i) with the same caption id are excluded from both cross-entropies
+    (reference _get_mask, :506-530); loss within 1e-4, gradients within 1e-3 of the fp64 oracle."""
+    dev = torch.device("cuda:0")
+    I, T = O.make_embeddings(n, d, rho=0.35, seed=21)
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, n_captions, (n,), generator=g)
+    Ic = I.to(dev).requires_grad_(True)
+    Tc = T.to(dev).requires_grad_(True)
+    lsc = torch.tensor([ls], dtype=torch.float64, device=dev, requires_grad=True)
+    loss, il, tl = VF.fused_clip_loss_from_embeddings(Ic, Tc, lsc, caption_ids=ids.to(dev))
+    loss.backward()
+    torch.cuda.synchronize()
+    ref = O.masked_loss_and_grads_from_embeddings(I, T, torch.tensor([ls], dtype=torch.float64), ids)
+    unmasked = O.closed_form(I.numpy(), T.numpy(), ls)
+    assert abs(float(ref["loss"]) - unmasked["loss"]) > 2e-4 * unmasked["loss"]      # the mask matters here
+    for k, v in (("loss", loss), ("image_loss", il), ("text_loss", tl)):
+        assert abs(v.item() - float(ref[k])) <= LOSS_RTOL * abs(float(ref[k])), k
+    assert O.rel_err(Ic.grad.cpu().numpy(), ref["dI"].numpy()) < GRAD_RTOL
+    assert O.rel_err(Tc.grad.cpu().numpy(), ref["dT"].numpy()) < GRAD_RTOL
+    assert abs(lsc.grad.item() - float(ref["dlogit_scale"])) <= GRAD_RTOL * abs(float(ref["dlogit_scale"]))
+    # all captions distinct: exactly the unmasked loss
+    Ic.grad = Tc.grad = lsc.grad = None
+    loss_u, _, _ = VF.fused_clip_loss_from_embeddings(Ic, Tc, lsc, caption_ids=torch.arange(n, device=dev))
+    plain, _, _ = VF.fused_clip_loss_from_embeddings(Ic, Tc, lsc)
+    assert loss_u.item() == plain.item()
+
+
 def test_errors_are_raised_not_swallowed(VF):
     dev = torch.device("cuda:0")
     I, T = O.make_embeddings(16, 16)

@@ -58,6 +58,14 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
                                   c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                   c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vlpclip_grad_both_masked": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                                         c_int, c_float, c_float, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                         c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_size_t, c_void_p]),
+    "vlpclip_lse_fwd_fused_masked": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vlpclip_grad_both_plan": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                        c_void_p, c_void_p, c_int, c_void_p]),
     "vlpclip_retrieval_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -70,6 +70,8 @@ struct GradBothParams {
   int* done_t;           // ... the dT consumers
   int* col_turn;         // [total_tiles]: rank of the piece that may add to the column next
   int np;                // producer slots (= s.np)
+  const int* xid;        // optional duplicate-caption mask: caption ids of the rows ...
+  const int* yid;        // ... and of the columns (G = 0 where they agree off the diagonal)
   Sched s;
 };
 
@@ -155,10 +157,13 @@ struct ProdIter {
 };
 
 // ---- softmax of NC logits of one row (see softmax_tile / softmax_tile_fast in grad_bwd.cu) -------
-template <bool kDiag, int NC>
+// kMask: entries whose column caption id (idv) equals the row's (my_id) are not negatives: G = 0
+// (the positive pair itself is set afterwards by kDiag)
+template <bool kDiag, bool kMask, int NC>
 __device__ __forceinline__ void gb_softmax(const uint32_t (&v)[NC], const float4* __restrict__ ymax4,
                                            const float4* __restrict__ ylg4, float xmax, float xlg,
                                            float scale_log2, float diag_val, int diag_j,
+                                           const int* __restrict__ yid, int my_id,
                                            uint32_t (&out)[NC / 2], float& ds_acc) {
 #pragma unroll
   for (int q = 0; q < NC / 4; ++q) {
@@ -166,6 +171,11 @@ __device__ __forceinline__ void gb_softmax(const uint32_t (&v)[NC], const float4
     const float4 yl = __ldg(ylg4 + q);
     const float ymv[4] = {ym.x, ym.y, ym.z, ym.w};
     const float ylv[4] = {yl.x, yl.y, yl.z, yl.w};
+    int idv[4] = {0, 0, 0, 0};
+    if (kMask) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) idv[e] = __ldg(yid + q * 4 + e);
+    }
     float g[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -174,6 +184,7 @@ __device__ __forceinline__ void gb_softmax(const uint32_t (&v)[NC], const float4
       const float a = ex2_approx(fmaf(s - xmax, scale_log2, -xlg));
       const float b = ex2_approx(fmaf(s - ymv[e], scale_log2, -ylv[e]));
       float gg = a + b;
+      if (kMask) gg = idv[e] == my_id ? 0.f : gg;
       if (kDiag) gg = (j == diag_j) ? diag_val : gg;
       ds_acc = fmaf(gg, s, ds_acc);
       g[e] = gg * G_SCALE;
@@ -182,15 +193,21 @@ __device__ __forceinline__ void gb_softmax(const uint32_t (&v)[NC], const float4
     out[q * 2 + 1] = pack_f16x2(g[2], g[3]);
   }
 }
-template <bool kDiag, int NC>
+template <bool kDiag, bool kMask, int NC>
 __device__ __forceinline__ void gb_softmax_fast(const uint32_t (&v)[NC], const float4* __restrict__ yc4,
                                                 float xmax, float xlg13, float xr, float scale_log2,
                                                 float diag_val_scaled, int diag_j,
+                                                const int* __restrict__ yid, int my_id,
                                                 uint32_t (&out)[NC / 2], float& ds_acc) {
 #pragma unroll
   for (int q = 0; q < NC / 4; ++q) {
     const float4 yc = __ldg(yc4 + q);
     const float ycv[4] = {yc.x, yc.y, yc.z, yc.w};
+    int idv[4] = {0, 0, 0, 0};
+    if (kMask) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) idv[e] = __ldg(yid + q * 4 + e);
+    }
     float g[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -198,6 +215,7 @@ __device__ __forceinline__ void gb_softmax_fast(const uint32_t (&v)[NC], const f
       const float s = __uint_as_float(v[j]);
       const float a = ex2_approx(fmaf(s - xmax, scale_log2, -xlg13));
       float gg = fmaf(a, xr * ycv[e], a);
+      if (kMask) gg = idv[e] == my_id ? 0.f : gg;
       if (kDiag) gg = (j == diag_j) ? diag_val_scaled : gg;
       ds_acc = fmaf(gg, s, ds_acc);
       g[e] = gg;
@@ -523,6 +541,7 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
         const float xlg = p.xlg[row];
         const float xr = p.xr[row];
         const int dcol = row_ok ? row - p.diag_shift : -1000000000;
+        const int my_id = (P.xid != nullptr && row_ok) ? __ldg(P.xid + row) : -1;
         float ds_acc = 0.f;
 
         for (int u = 0; u < ph.cs; ++u) {
@@ -546,25 +565,44 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
           const bool any_diag = __any_sync(0xffffffffu, has_diag);
           float diag_val = 0.f;
           if (has_diag) diag_val = -(p.w_row * p.xq[row] + p.w_col * p.yq[dcol]);
+          // (the padded statistics give P = 0 beyond n_cols; the caption ids are padded to whole tiles)
+          const bool masked = P.yid != nullptr;
+          const int* yid = masked ? P.yid + col0 : nullptr;
           if (fast) {
             const float4* yc4 = reinterpret_cast<const float4*>(p.yc + col0);
             float acc = 0.f;
-            if (any_diag)
-              gb_softmax_fast<true, GB_SMX_COLS>(v, yc4, xmax, xlg - 13.f, xr, scale_log2,
-                                                 diag_val * G_SCALE, diag_j, out, acc);
-            else
-              gb_softmax_fast<false, GB_SMX_COLS>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, 0.f, diag_j,
-                                                  out, acc);
+            if (masked) {
+              if (any_diag)
+                gb_softmax_fast<true, true, GB_SMX_COLS>(v, yc4, xmax, xlg - 13.f, xr, scale_log2,
+                                                         diag_val * G_SCALE, diag_j, yid, my_id, out, acc);
+              else
+                gb_softmax_fast<false, true, GB_SMX_COLS>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, 0.f,
+                                                          diag_j, yid, my_id, out, acc);
+            } else if (any_diag) {
+              gb_softmax_fast<true, false, GB_SMX_COLS>(v, yc4, xmax, xlg - 13.f, xr, scale_log2,
+                                                        diag_val * G_SCALE, diag_j, nullptr, 0, out, acc);
+            } else {
+              gb_softmax_fast<false, false, GB_SMX_COLS>(v, yc4, xmax, xlg - 13.f, xr, scale_log2, 0.f, diag_j,
+                                                         nullptr, 0, out, acc);
+            }
             ds_acc = fmaf(acc, 1.0f / G_SCALE, ds_acc);
           } else {
             const float4* ymax4 = reinterpret_cast<const float4*>(p.ymax + col0);
             const float4* ylg4 = reinterpret_cast<const float4*>(p.ylg + col0);
-            if (any_diag)
-              gb_softmax<true, GB_SMX_COLS>(v, ymax4, ylg4, xmax, xlg, scale_log2, diag_val, diag_j, out,
-                                            ds_acc);
-            else
-              gb_softmax<false, GB_SMX_COLS>(v, ymax4, ylg4, xmax, xlg, scale_log2, 0.f, diag_j, out,
-                                             ds_acc);
+            if (masked) {
+              if (any_diag)
+                gb_softmax<true, true, GB_SMX_COLS>(v, ymax4, ylg4, xmax, xlg, scale_log2, diag_val, diag_j, yid,
+                                                    my_id, out, ds_acc);
+              else
+                gb_softmax<false, true, GB_SMX_COLS>(v, ymax4, ylg4, xmax, xlg, scale_log2, 0.f, diag_j, yid,
+                                                     my_id, out, ds_acc);
+            } else if (any_diag) {
+              gb_softmax<true, false, GB_SMX_COLS>(v, ymax4, ylg4, xmax, xlg, scale_log2, diag_val, diag_j,
+                                                   nullptr, 0, out, ds_acc);
+            } else {
+              gb_softmax<false, false, GB_SMX_COLS>(v, ymax4, ylg4, xmax, xlg, scale_log2, 0.f, diag_j, nullptr,
+                                                    0, out, ds_acc);
+            }
           }
 
           // stage the fp16 G tile (K-major, 128B swizzle): the store warp must have read the slot's

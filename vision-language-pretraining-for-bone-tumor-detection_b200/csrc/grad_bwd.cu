@@ -874,7 +874,7 @@ static bool gb_roles(int n_sms, int* np_out, int* nq_out) {
 struct GbLayout {
   Sched s;
   int n_sms, np, nq;
-  size_t off_ds, off_parts, off_dy_part, off_ring, off_flags, flag_bytes, total;
+  size_t off_ds, off_parts, off_dy_part, off_ring, off_flags, flag_bytes, off_ids, total;
 };
 static bool gb_layout(int n_rows, int n_cols, int d, GbLayout& L) {
   const int nrb = (n_rows + 127) / 128, nt = (n_cols + 127) / 128;
@@ -894,6 +894,8 @@ static bool gb_layout(int n_rows, int n_cols, int d, GbLayout& L) {
   L.off_flags = o;
   L.flag_bytes = (3 * (size_t)L.np * GB_RING_DEPTH + (size_t)nt) * GB_FLAG_STRIDE * 4;
   o += align256(L.flag_bytes);
+  L.off_ids = o;                                   // column caption ids padded to whole tiles (masked loss)
+  o += align256((size_t)nt * 128 * 4);
   L.total = o + 1024;
   return true;
 }
@@ -1149,14 +1151,17 @@ size_t vlpclip_grad_both_workspace_bytes(int n_rows, int n_cols, int d) {
   return L.total;
 }
 
-int vlpclip_grad_both(const void* x, int ldx, const void* y, int ldy, const float* x_max,
-                      const float* x_lg2l, const float* x_q, const float* y_max,
-                      const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
-                      const float* scale, int diag_shift, int n_global, float w_row, float w_col,
-                      const float* out_mul, int dx_bf16, void* dx, int dy_bf16, void* dy,
-                      void* const* dy_owner_rows, int n_owners, int rows_per_owner, float* dscale,
-                      void* workspace, size_t workspace_bytes, void* stream_) {
+static int grad_both_impl(const void* x, int ldx, const void* y, int ldy, const float* x_max,
+                          const float* x_lg2l, const float* x_q, const float* y_max,
+                          const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
+                          const float* scale, int diag_shift, int n_global, float w_row, float w_col,
+                          const float* out_mul, int dx_bf16, void* dx, int dy_bf16, void* dy,
+                          void* const* dy_owner_rows, int n_owners, int rows_per_owner, float* dscale,
+                          const int* row_ids, const int* col_ids, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if ((row_ids == nullptr) != (col_ids == nullptr))
+    return fail(-1, "grad_both: row and column caption ids must be given together");
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "grad_both: empty problem (%d x %d)", n_rows, n_cols);
   if (!x || !y || !scale || !x_max || !x_lg2l || !x_q || !y_max || !y_lg2l || !y_q || !dx ||
       (!dy && !dy_owner_rows) || !workspace)
@@ -1253,6 +1258,13 @@ int vlpclip_grad_both(const void* x, int ldx, const void* y, int ldy, const floa
   P.np = L.np;
   P.s = L.s;
   P.dy_direct = (dy != nullptr && !dy_owner_rows && !dy_bf16) ? 1 : 0;
+  if (col_ids) {   // pad the column ids to whole tiles with a value no caption id (>= 0) can take
+    int* yid_pad = (int*)(base + L.off_ids);
+    VLP_CUDA_OK(cudaMemsetAsync(yid_pad, 0xFE, (size_t)npy * 4, stream));
+    VLP_CUDA_OK(cudaMemcpyAsync(yid_pad, col_ids, (size_t)n_cols * 4, cudaMemcpyDeviceToDevice, stream));
+    P.xid = row_ids;
+    P.yid = yid_pad;
+  }
   p.wait_prof = wait_prof_buffer();
 
   const float l2wr = log2f(w_row), l2wc = log2f(w_col);
@@ -1331,6 +1343,32 @@ int vlpclip_grad_both(const void* x, int ldx, const void* y, int ldy, const floa
     VLP_CUDA_OK(cudaGetLastError());
   }
   return 0;
+}
+
+int vlpclip_grad_both(const void* x, int ldx, const void* y, int ldy, const float* x_max,
+                      const float* x_lg2l, const float* x_q, const float* y_max,
+                      const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
+                      const float* scale, int diag_shift, int n_global, float w_row, float w_col,
+                      const float* out_mul, int dx_bf16, void* dx, int dy_bf16, void* dy,
+                      void* const* dy_owner_rows, int n_owners, int rows_per_owner, float* dscale,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  return grad_both_impl(x, ldx, y, ldy, x_max, x_lg2l, x_q, y_max, y_lg2l, y_q, n_rows, n_cols, d, scale,
+                        diag_shift, n_global, w_row, w_col, out_mul, dx_bf16, dx, dy_bf16, dy, dy_owner_rows,
+                        n_owners, rows_per_owner, dscale, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+int vlpclip_grad_both_masked(const void* x, int ldx, const void* y, int ldy, const float* x_max,
+                             const float* x_lg2l, const float* x_q, const float* y_max,
+                             const float* y_lg2l, const float* y_q, int n_rows, int n_cols, int d,
+                             const float* scale, int diag_shift, int n_global, float w_row, float w_col,
+                             const float* out_mul, int dx_bf16, void* dx, int dy_bf16, void* dy,
+                             void* const* dy_owner_rows, int n_owners, int rows_per_owner, float* dscale,
+                             const int* row_ids, const int* col_ids, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (!row_ids || !col_ids) return fail(-1, "grad_both_masked: null caption ids");
+  return grad_both_impl(x, ldx, y, ldy, x_max, x_lg2l, x_q, y_max, y_lg2l, y_q, n_rows, n_cols, d, scale,
+                        diag_shift, n_global, w_row, w_col, out_mul, dx_bf16, dx, dy_bf16, dy, dy_owner_rows,
+                        n_owners, rows_per_owner, dscale, row_ids, col_ids, workspace, workspace_bytes, stream);
 }
 
 // host-only: the schedule of the single-recompute backward for np producer slots / nq dT consumers.

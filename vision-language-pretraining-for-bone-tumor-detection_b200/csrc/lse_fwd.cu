@@ -65,6 +65,10 @@ struct LseParams {
   // sum_i exp2(k c_ij - ref) with a log2-domain reference `ref`; the positive pair is left out
   float* col_ref;       // [n_row_blocks][total_tiles * 128]
   float* col_l;         // [n_row_blocks][total_tiles * 128]
+  // duplicate-caption mask (optional): a logit whose row and column carry the same caption id is
+  // excluded from both soft-maxes unless it is the positive pair itself (reference _get_mask, :506-530)
+  const int* xid;       // [n_rows] caption id of the rows, or nullptr
+  const int* yid;       // [n_cols] caption id of the columns
   // retrieval modes: partial results per (chunk, column group), merged by rank_merge / topk_merge
   int* part_cnt;        // MODE_RANK [n_chunks * FWD_CG][n_rows]
   float* part_val;      // MODE_TOPK [n_chunks * FWD_CG][n_rows][RK]
@@ -329,6 +333,7 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
         continue;
       }
       float m_run = -INFINITY, mraw_run = -INFINITY, l_run = 0.f;
+      const int my_id = (p.xid != nullptr && row_ok) ? __ldg(p.xid + row) : -1;
       for (int t = t0; t < t1; ++t, ++tile_ctr) {
         const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
         const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
@@ -347,6 +352,25 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
 #pragma unroll
           for (int j = 0; j < FWD_CPT; ++j)
             if (col0 + j >= p.n_cols) v[j] = __float_as_uint(-INFINITY);
+        }
+        if (p.yid != nullptr) {   // duplicate captions: not negatives of this row (nor of that column)
+          if (col0 + FWD_CPT <= p.n_cols) {
+            const int4* y4 = reinterpret_cast<const int4*>(p.yid + col0);
+#pragma unroll
+            for (int q = 0; q < FWD_CPT / 4; ++q) {
+              const int4 w = __ldg(y4 + q);
+              const int c = col0 + q * 4;
+              if (w.x == my_id && c + 0 != dcol) v[q * 4 + 0] = __float_as_uint(-INFINITY);
+              if (w.y == my_id && c + 1 != dcol) v[q * 4 + 1] = __float_as_uint(-INFINITY);
+              if (w.z == my_id && c + 2 != dcol) v[q * 4 + 2] = __float_as_uint(-INFINITY);
+              if (w.w == my_id && c + 3 != dcol) v[q * 4 + 3] = __float_as_uint(-INFINITY);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < FWD_CPT; ++j)
+              if (col0 + j < p.n_cols && __ldg(p.yid + col0 + j) == my_id && col0 + j != dcol)
+                v[j] = __float_as_uint(-INFINITY);
+          }
         }
         float mx = __uint_as_float(v[0]);
 #pragma unroll
@@ -778,7 +802,8 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
                         int d, const float* scale, int diag_shift, float* row_max, float* row_l,
                         float* diag,
                         float* col_max, float* col_l, void* workspace, size_t workspace_bytes,
-                        cudaStream_t stream, bool operand_f16 = false) {
+                        cudaStream_t stream, bool operand_f16 = false, const int* row_ids = nullptr,
+                        const int* col_ids = nullptr) {
   const bool fused = col_max != nullptr;
   if (n_rows <= 0 || n_cols <= 0) return fail(-1, "lse_fwd: empty problem (%d x %d)", n_rows, n_cols);
   if (!x || !y || !scale || !row_max || !row_l || !diag || !workspace || (fused && !col_l))
@@ -809,6 +834,12 @@ static int lse_fwd_impl(const void* x, int ldx, const void* y, int ldy, int n_ro
   pick_chunks(p.n_row_blocks, p.total_tiles, nsm, &p.n_chunks, &p.tiles_per_chunk);
   p.diag_shift = diag_shift;
   p.scale_ptr = scale;
+  if ((row_ids == nullptr) != (col_ids == nullptr))
+    return fail(-1, "lse_fwd: row and column caption ids must be given together");
+  if (col_ids && (reinterpret_cast<uintptr_t>(col_ids) & 15) != 0)
+    return fail(-1, "lse_fwd: column caption ids must be 16-byte aligned");
+  p.xid = row_ids;
+  p.yid = col_ids;
   const int nparts = p.n_chunks * FWD_CG;
   p.part_m = (float*)workspace;
   p.part_l = p.part_m + (size_t)nparts * n_rows;
@@ -965,6 +996,18 @@ int vlpclip_lse_fwd_fused(const void* x, int ldx, const void* y, int ldy, int n_
   if (!col_max || !col_l) return fail(-1, "lse_fwd_fused: null column outputs");
   return lse_fwd_impl(x, ldx, y, ldy, n_rows, n_cols, d, scale, diag_shift, row_max, row_l, diag,
                       col_max, col_l, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+int vlpclip_lse_fwd_fused_masked(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,
+                                 int d, int operand_f16, const float* scale, int diag_shift,
+                                 const int* row_ids, const int* col_ids, float* row_max, float* row_l,
+                                 float* diag, float* col_max, float* col_l, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+  if (!col_max || !col_l) return fail(-1, "lse_fwd_fused_masked: null column outputs");
+  if (!row_ids || !col_ids) return fail(-1, "lse_fwd_fused_masked: null caption ids");
+  return lse_fwd_impl(x, ldx, y, ldy, n_rows, n_cols, d, scale, diag_shift, row_max, row_l, diag,
+                      col_max, col_l, workspace, workspace_bytes, (cudaStream_t)stream_,
+                      operand_f16 != 0, row_ids, col_ids);
 }
 
 int vlpclip_lse_fwd_f16(const void* x, int ldx, const void* y, int ldy, int n_rows, int n_cols,

@@ -162,9 +162,18 @@ def lse_stats(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shi
     return row_max, row_l, diag
 
 
-def lse_stats_fused(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shift: int = 0):
+def _as_ids(ids: torch.Tensor, n: int, device, name: str) -> torch.Tensor:
+    if ids.numel() != n:
+        raise ValueError(f"{name}: expected {n} caption ids, got {ids.numel()}")
+    return ids.detach().to(device=device, dtype=torch.int32).reshape(n).contiguous()
+
+
+def lse_stats_fused(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, diag_shift: int = 0,
+                    row_ids: Optional[torch.Tensor] = None, col_ids: Optional[torch.Tensor] = None):
     """One sweep over ``scale * x @ y.T``: row statistics (as ``lse_stats``) plus the statistics of
-    every column over the given rows: (row_max, row_l, diag, col_ref, col_l)."""
+    every column over the given rows: (row_max, row_l, diag, col_ref, col_l).  ``row_ids`` /
+    ``col_ids`` (caption ids >= 0): logits whose row and column ids agree are excluded from both
+    directions unless they are the positive pair (duplicate-caption mask)."""
     _require_cuda(x_bf16, "x")
     _require_cuda(y_bf16, "y")
     if x_bf16.dtype != y_bf16.dtype or x_bf16.dtype not in (torch.bfloat16, torch.float16):
@@ -185,6 +194,17 @@ def lse_stats_fused(x_bf16: torch.Tensor, y_bf16: torch.Tensor, scale: float, di
     col_l = torch.empty(n_cols, dtype=torch.float32, device=dev)
     nbytes = lib.vlpclip_lse_fused_workspace_bytes(n_rows, n_cols, d)
     ws = _ws(nbytes, dev)
+    if (row_ids is None) != (col_ids is None):
+        raise ValueError("row_ids and col_ids must be given together")
+    if row_ids is not None:
+        rid, cid = _as_ids(row_ids, n_rows, dev, "row_ids"), _as_ids(col_ids, n_cols, dev, "col_ids")
+        rc = lib.vlpclip_lse_fwd_fused_masked(
+            x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows, n_cols, d,
+            1 if x.dtype == torch.float16 else 0, sc.data_ptr(), int(diag_shift), rid.data_ptr(),
+            cid.data_ptr(), row_max.data_ptr(), row_l.data_ptr(), diag.data_ptr(), col_max.data_ptr(),
+            col_l.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        _lib.check(rc, "lse_fwd_fused_masked")
+        return row_max, row_l, diag, col_max, col_l
     fn = lib.vlpclip_lse_fwd_fused_f16 if x.dtype == torch.float16 else lib.vlpclip_lse_fwd_fused
     rc = fn(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), n_rows, n_cols, d, sc.data_ptr(),
             int(diag_shift), row_max.data_ptr(), row_l.data_ptr(), diag.data_ptr(),
@@ -271,8 +291,10 @@ def _grad(x_f16, y_f16, x_stats, y_stats, scale: float, diag_shift: int, n_globa
 def _grad_both(x_f16, y_f16, x_stats, y_stats, scale, diag_shift: int, n_global: int,
                w_row: float = 1.0, w_col: float = 1.0, want_dscale: bool = False,
                out_mul: Optional[torch.Tensor] = None, out_dtypes=(torch.float32, torch.float32),
-               window: "Optional[PeerWindow]" = None):
+               window: "Optional[PeerWindow]" = None, row_ids: Optional[torch.Tensor] = None,
+               col_ids: Optional[torch.Tensor] = None):
     """Single-recompute backward: (dX, dY | parity, dscale) from ONE sweep over the logit tiles.
+    ``row_ids`` / ``col_ids``: duplicate-caption mask (the statistics must come from the masked forward).
 
     Without ``window`` dY is returned as a tensor; with a peer window the final dY rows are stored
     into the owning ranks' windows (fused reduce-scatter) and the window parity is returned instead
@@ -295,16 +317,19 @@ def _grad_both(x_f16, y_f16, x_stats, y_stats, scale, diag_shift: int, n_global:
         dy = None
         parity = window.next_parity()
         owners, n_owners, rows_per_owner, second = window.owner_rows(parity), window.world, window.rows, parity
-    rc = lib.vlpclip_grad_both(
-        x_f16.data_ptr(), x_f16.stride(0), y_f16.data_ptr(), y_f16.stride(0),
-        x_stats[0].data_ptr(), x_stats[1].data_ptr(), x_stats[2].data_ptr(),
-        y_stats[0].data_ptr(), y_stats[1].data_ptr(), y_stats[2].data_ptr(),
-        n_rows, n_cols, d, sc.data_ptr(), int(diag_shift), int(n_global), float(w_row), float(w_col),
-        out_mul.data_ptr() if out_mul is not None else None,
-        1 if out_dtypes[0] == torch.bfloat16 else 0, dx.data_ptr(),
-        1 if out_dtypes[1] == torch.bfloat16 else 0, dy.data_ptr() if dy is not None else None,
-        owners, n_owners, rows_per_owner, ds.data_ptr() if want_dscale else None, ws.data_ptr(),
-        nbytes, _stream())
+    common = (x_f16.data_ptr(), x_f16.stride(0), y_f16.data_ptr(), y_f16.stride(0),
+              x_stats[0].data_ptr(), x_stats[1].data_ptr(), x_stats[2].data_ptr(),
+              y_stats[0].data_ptr(), y_stats[1].data_ptr(), y_stats[2].data_ptr(),
+              n_rows, n_cols, d, sc.data_ptr(), int(diag_shift), int(n_global), float(w_row), float(w_col),
+              out_mul.data_ptr() if out_mul is not None else None,
+              1 if out_dtypes[0] == torch.bfloat16 else 0, dx.data_ptr(),
+              1 if out_dtypes[1] == torch.bfloat16 else 0, dy.data_ptr() if dy is not None else None,
+              owners, n_owners, rows_per_owner, ds.data_ptr() if want_dscale else None)
+    if row_ids is not None:
+        rid, cid = _as_ids(row_ids, n_rows, dev, "row_ids"), _as_ids(col_ids, n_cols, dev, "col_ids")
+        rc = lib.vlpclip_grad_both_masked(*common, rid.data_ptr(), cid.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    else:
+        rc = lib.vlpclip_grad_both(*common, ws.data_ptr(), nbytes, _stream())
     _lib.check(rc, "grad_both")
     return dx, second, ds
 
@@ -554,8 +579,8 @@ class CudaOps:
         return lse_stats(x, y, scale, diag_shift)
 
     @staticmethod
-    def lse_stats_fused(x, y, scale, diag_shift):
-        return lse_stats_fused(x, y, scale, diag_shift)
+    def lse_stats_fused(x, y, scale, diag_shift, row_ids=None, col_ids=None):
+        return lse_stats_fused(x, y, scale, diag_shift, row_ids, col_ids)
 
     @staticmethod
     def merge_stats(part_max, part_l, diag, scale):
@@ -577,9 +602,10 @@ class CudaOps:
 
     @staticmethod
     def grad_both(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col, want_dscale,
-                  out_mul=None, out_dtypes=(torch.float32, torch.float32), window=None):
+                  out_mul=None, out_dtypes=(torch.float32, torch.float32), window=None, row_ids=None,
+                  col_ids=None):
         return _grad_both(x, y, x_stats, y_stats, scale, diag_shift, n_global, w_row, w_col,
-                          want_dscale, out_mul, out_dtypes, window)
+                          want_dscale, out_mul, out_dtypes, window, row_ids, col_ids)
 
     @staticmethod
     def to_backward_operand(x_bf16):
@@ -601,7 +627,7 @@ class _FusedClipLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, image_embeddings, text_embeddings, logit_scale, i_bf16, t_bf16, i_f16, t_f16,
-                group, grad_scale):
+                group, grad_scale, caption_ids=None):
         ctx.set_materialize_grads(False)
         _require_cuda(image_embeddings, "image_embeddings")
         _require_cuda(text_embeddings, "text_embeddings")
@@ -652,9 +678,12 @@ class _FusedClipLoss(torch.autograd.Function):
                 t_.record_stream(side)
                 t_.record_stream(main)
 
+        if caption_ids is not None and EXACT_COLUMNS:
+            raise NotImplementedError("caption_ids need the fused column statistics (unset VLP_B200_EXACT_COLUMNS)")
         plan = sharded.forward_plan(CudaOps, i_bf16, t_bf16, scale, group,
-                                    exact_columns=EXACT_COLUMNS)
+                                    exact_columns=EXACT_COLUMNS, ids_loc=caption_ids)
         world = plan["world"]
+        ctx.ids = plan.get("ids")
         ctx.group = group
         ctx.world, ctx.rank = world, plan["rank"]
         ctx.n_loc, ctx.n_glob = n_loc, plan["n_glob"]
@@ -680,7 +709,7 @@ class _FusedClipLoss(torch.autograd.Function):
         r_stats, c_stats = (r_max, r_lg, r_q), (c_max, c_lg, c_q)
         need_i, need_t, need_ls = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         if not (need_i or need_t or need_ls) or (g_loss is None and g_il is None and g_tl is None):
-            return (None,) * 9
+            return (None,) * 10
         # direction weights: d/dS = (w_r P_row + w_c P_col - (w_r + w_c) delta) / (2N)
         mul = None
         if g_il is None and g_tl is None:
@@ -696,7 +725,7 @@ class _FusedClipLoss(torch.autograd.Function):
                     raise NotImplementedError("mixed-sign upstream gradients for image/text loss")
                 w_r, w_c, sign = -w_r, -w_c, -1.0
             if w_r == 0.0 and w_c == 0.0:
-                return (None,) * 9
+                return (None,) * 10
             mul = torch.tensor(sign, dtype=torch.float32, device=i_bf16.device)
 
         i_f16, t_f16 = ctx.f16
@@ -717,7 +746,7 @@ class _FusedClipLoss(torch.autograd.Function):
             CudaOps, i_f16, t_all_f16, r_stats, c_stats, ctx.scale, ctx.n_loc, ctx.n_glob, ctx.rank,
             world, ctx.group, w_r, w_c, need_i, need_t, need_ls, out_mul=mul,
             out_dtypes=(kdt(ctx.in_dtypes[0]), kdt(ctx.in_dtypes[1])),
-            tail_barrier=ctx.tail_barrier, single_sweep=SINGLE_SWEEP)
+            tail_barrier=ctx.tail_barrier, single_sweep=SINGLE_SWEEP, ids=ctx.ids)
         d_ls = None
         if need_ls:
             d_ls = ds * ctx.dscale_dls                      # chain rule through exp + clamp (:456-457)
@@ -726,7 +755,7 @@ class _FusedClipLoss(torch.autograd.Function):
             d_i = d_i.to(ctx.in_dtypes[0])
         if need_t and d_t.dtype != ctx.in_dtypes[1]:
             d_t = d_t.to(ctx.in_dtypes[1])
-        return d_i, d_t, d_ls, None, None, None, None, None, None
+        return d_i, d_t, d_ls, None, None, None, None, None, None, None
 
 
 
@@ -916,7 +945,7 @@ class _FusedClipLossGraphed(torch.autograd.Function):
 
 def fused_clip_loss_from_embeddings(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor,
                                     logit_scale: torch.Tensor, *, group=None,
-                                    grad_scale: float = 1.0,
+                                    grad_scale: float = 1.0, caption_ids: Optional[torch.Tensor] = None,
                                     _operands=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Symmetric InfoNCE loss of already L2-normalised embeddings.
 
@@ -925,15 +954,18 @@ def fused_clip_loss_from_embeddings(image_embeddings: torch.Tensor, text_embeddi
     ``(loss, image_loss, text_loss)``.  The embeddings are consumed as bf16 (values that are
     bf16-representable are used exactly); accumulation is fp32.  ``group``: torch.distributed
     process group for the sharded global-batch variant (each rank passes its local rows);
-    ``grad_scale`` multiplies every gradient (use ``world_size`` under DDP gradient averaging).
+    ``grad_scale`` multiplies the embedding gradients (use ``world_size`` under DDP gradient averaging).
+    ``caption_ids`` (int tensor [batch], ids >= 0, globally consistent across ranks): duplicate-caption
+    mask -- pairs (i, j != i) with the same caption id are excluded from both cross-entropies instead of
+    being treated as negatives (the mask of the reference's ``_get_mask``, lines 506-530).
     """
     with _device_guard(image_embeddings, text_embeddings, logit_scale):
         return _fused_clip_loss_from_embeddings(image_embeddings, text_embeddings, logit_scale, group,
-                                                grad_scale, _operands)
+                                                grad_scale, _operands, caption_ids)
 
 
 def _fused_clip_loss_from_embeddings(image_embeddings, text_embeddings, logit_scale, group, grad_scale,
-                                     _operands):
+                                     _operands, caption_ids=None):
     i_bf16 = t_bf16 = i_f16 = t_f16 = None
     if _operands is not None:
         i_bf16, t_bf16, i_f16, t_f16 = _operands
@@ -943,12 +975,17 @@ def _fused_clip_loss_from_embeddings(image_embeddings, text_embeddings, logit_sc
     needs_grad = torch.is_grad_enabled() and (image_embeddings.requires_grad or
                                               text_embeddings.requires_grad or
                                               logit_scale.requires_grad)
-    if _use_graph(world, needs_grad) and image_embeddings.is_cuda and image_embeddings.dim() == 2 \
+    if caption_ids is not None:
+        if caption_ids.numel() != image_embeddings.shape[0]:
+            raise ValueError(f"caption_ids: expected {image_embeddings.shape[0]} ids, got {caption_ids.numel()}")
+        caption_ids = caption_ids.detach().to(device=image_embeddings.device, dtype=torch.int32).contiguous()
+    if caption_ids is None and _use_graph(world, needs_grad) and image_embeddings.is_cuda \
+            and image_embeddings.dim() == 2 \
             and image_embeddings.shape == text_embeddings.shape and logit_scale.numel() == 1:
         return _FusedClipLossGraphed.apply(image_embeddings, text_embeddings, logit_scale, group,
                                            grad_scale)
     return _FusedClipLoss.apply(image_embeddings, text_embeddings, logit_scale, i_bf16, t_bf16,
-                                i_f16, t_f16, group, grad_scale)
+                                i_f16, t_f16, group, grad_scale, caption_ids)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -1038,7 +1075,8 @@ def project_normalize(features: torch.Tensor, projection: torch.Tensor, out_bf16
 
 def fused_clip_loss(image_features: torch.Tensor, text_features: torch.Tensor,
                     image_projection: torch.Tensor, text_projection: torch.Tensor,
-                    logit_scale: torch.Tensor, *, group=None, grad_scale: float = 1.0):
+                    logit_scale: torch.Tensor, *, group=None, grad_scale: float = 1.0,
+                    caption_ids: Optional[torch.Tensor] = None):
     """Full head: returns (loss, image_loss, text_loss, image_embeddings, text_embeddings).
 
     Same results as the reference ``forward`` (:448-459) + ``_compute_loss`` (:533-552) on the
@@ -1047,7 +1085,7 @@ def fused_clip_loss(image_features: torch.Tensor, text_features: torch.Tensor,
     i_emb, i_bf16, i_f16 = project_normalize(image_features, image_projection)
     t_emb, t_bf16, t_f16 = project_normalize(text_features, text_projection)
     loss, il, tl = fused_clip_loss_from_embeddings(
-        i_emb, t_emb, logit_scale, group=group, grad_scale=grad_scale,
+        i_emb, t_emb, logit_scale, group=group, grad_scale=grad_scale, caption_ids=caption_ids,
         _operands=(i_bf16, t_bf16, i_f16, t_f16))
     return loss, il, tl, i_emb, t_emb
 

@@ -252,6 +252,10 @@ class VisionLanguageModule(_LightningBase):
 
         # fused-head options (extra kwargs, absent from the reference's signature)
         self.share_negatives_across_ranks = bool(kwargs.get("share_negatives_across_ranks", True))
+        # mask_duplicate_captions=True: samples of a batch that carry the same caption string are not
+        # used as negatives of one another (fused duplicate-caption mask).  The
+        # reference's deduplicate / masked_loss flags keep raising like the reference.
+        self.mask_duplicate_captions = bool(kwargs.get("mask_duplicate_captions", False))
 
         self.image_encoder = ImageEncoder(image_model, drop_rate=image_encoder_droupout)
         self.text_encoder = TextEncoder(text_encoder_model)
@@ -370,10 +374,21 @@ class VisionLanguageModule(_LightningBase):
             # of the reference's samplers may differ): this step falls back to the reference's own
             # DDP semantics, the loss over the local pairs
             group, world = None, 1
+        caption_ids = None
+        if self.mask_duplicate_captions and captions is not None:
+            caption_ids = self._caption_ids(captions, logits.device)
         loss, image_loss, text_loss = VF.fused_clip_loss_from_embeddings(
             logits.image_embeddings, logits.text_embeddings, logits.logit_scale, group=group,
-            grad_scale=float(world), _operands=logits.operands)
+            grad_scale=float(world), caption_ids=caption_ids, _operands=logits.operands)
         return loss, image_loss, text_loss
+
+    @staticmethod
+    def _caption_ids(captions, device) -> torch.Tensor:
+        """Caption strings -> non-negative int32 ids that agree across ranks without communication
+        (crc32 of the text; the reference numbers them with np.unique per batch, :482)."""
+        import zlib
+        ids = [zlib.crc32(str(c).encode("utf-8")) & 0x7FFFFFFF for c in captions]
+        return torch.tensor(ids, dtype=torch.int32, device=device)
 
     @staticmethod
     def _equal_shards(n_loc: int, group) -> bool:

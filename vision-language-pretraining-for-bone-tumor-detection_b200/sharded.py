@@ -64,7 +64,7 @@ def all_gather_rows(t: torch.Tensor, group, world: int) -> torch.Tensor:
     return out
 
 
-def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: bool = False):
+def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: bool = False, ids_loc=None):
     """Returns a dict with the three losses (device scalars) and everything backward needs.
 
     When ``ops`` offers ``lse_stats_fused`` (and ``exact_columns`` is False) the row and the column
@@ -84,7 +84,17 @@ def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: boo
         t_all = all_gather_rows(t_loc, group, world) if world > 1 else t_loc
 
     fused = (not exact_columns) and hasattr(ops, "lse_stats_fused")
-    if fused:
+    ids = None
+    if ids_loc is not None:
+        # duplicate-caption mask: ids of the local rows and of ALL columns (one small all-gather)
+        if not fused:
+            raise NotImplementedError("caption ids need the fused statistics sweep")
+        ids_all = all_gather_rows(ids_loc, group, world) if world > 1 else ids_loc
+        ids = (ids_loc, ids_all)
+    if fused and ids is not None:
+        r_max_p, r_l_p, r_diag, c_max_p, c_l_p = ops.lse_stats_fused(i_loc, t_all, scale, -lo, ids[0], ids[1])
+        c_diag_own = r_diag
+    elif fused:
         # one sweep: rows of S owned by the local images (complete) + partial column statistics
         r_max_p, r_l_p, r_diag, c_max_p, c_l_p = ops.lse_stats_fused(i_loc, t_all, scale, -lo)
         c_diag_own = r_diag                     # S_jj seen from column j is the same logit
@@ -116,14 +126,14 @@ def forward_plan(ops, i_loc, t_loc, scale: float, group=None, exact_columns: boo
         l3 = torch.stack([(losses[0] + losses[1]) * 0.5, losses[0], losses[1]])   # reference :552
     return {"loss": l3[0], "image_loss": l3[1], "text_loss": l3[2], "losses": l3,
             "t_all": t_all, "bwd_operands": pushed, "r_stats": (r_max, r_lg, r_q), "c_stats": (c_max, c_lg, c_q),
-            "world": world, "rank": rank, "n_loc": n_loc, "n_glob": n_glob}
+            "world": world, "rank": rank, "n_loc": n_loc, "n_glob": n_glob, "ids": ids}
 
 
 def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc: int, n_glob: int,
                   rank: int, world: int, group=None, w_row: float = 1.0, w_col: float = 1.0,
                   need_i: bool = True, need_t: bool = True, need_scale: bool = True,
                   out_mul=None, out_dtypes=(torch.float32, torch.float32), tail_barrier=False,
-                  single_sweep=True):
+                  single_sweep=True, ids=None):
     """(dI_loc, dT_loc, dscale) of the global loss; operands are the backward copies.
 
     ``out_mul`` (device scalar) multiplies dI and dT (not dscale); where a gradient is final on this
@@ -134,11 +144,17 @@ def backward_plan(ops, i_loc_op, t_all_op, r_stats, c_stats, scale: float, n_loc
     window = None
     if need_t and world > 1 and hasattr(ops, "peer_window"):
         window = ops.peer_window(group, world, rank, n_loc, t_all_op.shape[1], t_all_op.device)
-    if single_sweep and need_i and need_t and hasattr(ops, "grad_both") and (world == 1 or window is not None):
+    one_sweep = (single_sweep or ids is not None) and need_i and need_t and hasattr(ops, "grad_both") \
+        and (world == 1 or window is not None)
+    if ids is not None and not one_sweep:
+        raise NotImplementedError("the duplicate-caption mask is implemented in the single-recompute backward only "
+                                  "(needs gradients for both embedding streams and, when sharded, peer windows)")
+    if one_sweep:
         # ONE sweep over the logit tiles feeds both accumulations (8 N^2 D executed flops per step
         # instead of 10 N^2 D); with peer windows the dT rows leave through the fused reduce-scatter
+        extra = {} if ids is None else {"row_ids": ids[0], "col_ids": ids[1]}
         d_i, second, ds = ops.grad_both(i_loc_op, t_all_op, r_stats, c_stats, scale, -lo, n_glob, w_row,
-                                        w_col, need_scale, out_mul, out_dtypes, window)
+                                        w_col, need_scale, out_mul, out_dtypes, window, **extra)
         if window is None:
             d_t = second
         else:
