@@ -29,10 +29,21 @@ if PROF:   # a second build of the library with per-role blocked-cycle counters
         sys.exit(0)
     _build.LIB_PATH = prof_lib
     _build.needs_build = lambda: False
+TIME_ONLY = "--time-only" in sys.argv      # skip the parity part (diagnostic builds give wrong results)
+if TIME_ONLY:
+    sys.argv.remove("--time-only")
+if "--lib" in sys.argv:                    # a library built by hand (tools/diag_build.sh)
+    i = sys.argv.index("--lib")
+    _build.LIB_PATH = os.path.abspath(sys.argv[i + 1])
+    _build.needs_build = lambda: False
+    del sys.argv[i:i + 2]
+    PROF = PROF or "prof" in os.path.basename(_build.LIB_PATH)
 from vlp_b200 import functional as VF  # noqa: E402
 
 PROD_NAMES = {0: "P.tma wait ring stage free", 1: "P.mma wait X staged", 2: "P.mma wait S buffer free",
               3: "P.mma wait Y stage full", 4: "P.smx wait S tile ready", 6: "P.smx wait G slot stored",
+              5: "P.smx tmem ld + release S (sect.)", 7: "P.smx proxy fence + arrive (sect.)",
+              13: "P.smx softmax arithmetic (sect.)", 14: "P.mma issue region, 4 stages (sect.)",
               8: "P.st  wait G staged", 9: "P.st  poll ring slot fetched", 10: "P.st  store read smem",
               11: "P.st  store complete", 12: "P.st  publish"}
 DI_NAMES = {0: "I.tma wait G slot free", 1: "I.tma fetch G (poll + issue)", 2: "I.tma wait ring stage free",
@@ -127,6 +138,8 @@ def main():
     s = 1 / 0.07
     ok = True
     for nn, dd in [(128, 64), (100, 72), (256, 512), (1000, 128), (2048, 256), (4096, 512), (6500, 512), (3000, 768)]:
+        if TIME_ONLY:
+            break
         ok = parity(nn, dd, dev, s) and ok
     I, T = make(n, d, dev)
     r, c = stats(I, T, s)
@@ -153,7 +166,7 @@ def main():
         wait_profile(lib, lambda: VF._grad_both(i16, t16, r[:3], c[:3], s, 0, n, 1.0, 1.0, True),
                      ((n + 127) // 128) ** 2)
     for R in (4096, 8192, 16384):
-        if R >= n:
+        if R >= n or TIME_ONLY:
             continue
         Il, il16 = I[:R], i16[:R]
         rm, rl, rdiag, cm, cl = VF.lse_stats_fused(Il, T, s, 0)

@@ -172,9 +172,12 @@ __device__ __forceinline__ void gb_softmax(const uint32_t (&v)[NC], const float4
     const float ymv[4] = {ym.x, ym.y, ym.z, ym.w};
     const float ylv[4] = {yl.x, yl.y, yl.z, yl.w};
     int idv[4] = {0, 0, 0, 0};
-    if (kMask) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) idv[e] = __ldg(yid + q * 4 + e);
+    if (kMask) {   // (column ids are padded to whole tiles and 16-byte aligned: one load per 4 columns)
+      const int4 iv = __ldg(reinterpret_cast<const int4*>(yid) + q);
+      idv[0] = iv.x;
+      idv[1] = iv.y;
+      idv[2] = iv.z;
+      idv[3] = iv.w;
     }
     float g[4];
 #pragma unroll
@@ -193,27 +196,38 @@ __device__ __forceinline__ void gb_softmax(const uint32_t (&v)[NC], const float4
     out[q * 2 + 1] = pack_f16x2(g[2], g[3]);
   }
 }
+// (the exponent k (s - xmax) - xlg13 is evaluated as fma(s, k, c) with c = -(k xmax + xlg13) formed once
+// per row: one instruction less per logit; |k s| <= ~150, so the fp32 rounding of the product moves the
+// exponent by < 1e-5, far below the fp16 rounding of G)
 template <bool kDiag, bool kMask, int NC>
 __device__ __forceinline__ void gb_softmax_fast(const uint32_t (&v)[NC], const float4* __restrict__ yc4,
                                                 float xmax, float xlg13, float xr, float scale_log2,
                                                 float diag_val_scaled, int diag_j,
                                                 const int* __restrict__ yid, int my_id,
                                                 uint32_t (&out)[NC / 2], float& ds_acc) {
+  const float c_row = -fmaf(xmax, scale_log2, xlg13);
 #pragma unroll
   for (int q = 0; q < NC / 4; ++q) {
     const float4 yc = __ldg(yc4 + q);
     const float ycv[4] = {yc.x, yc.y, yc.z, yc.w};
     int idv[4] = {0, 0, 0, 0};
-    if (kMask) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) idv[e] = __ldg(yid + q * 4 + e);
+    if (kMask) {   // (column ids are padded to whole tiles and 16-byte aligned: one load per 4 columns)
+      const int4 iv = __ldg(reinterpret_cast<const int4*>(yid) + q);
+      idv[0] = iv.x;
+      idv[1] = iv.y;
+      idv[2] = iv.z;
+      idv[3] = iv.w;
     }
     float g[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = q * 4 + e;
       const float s = __uint_as_float(v[j]);
-      const float a = ex2_approx(fmaf(s - xmax, scale_log2, -xlg13));
+#ifdef GB_DIAG_NO_EX2
+      const float a = fmaf(s, scale_log2, c_row);
+#else
+      const float a = ex2_approx(fmaf(s, scale_log2, c_row));
+#endif
       float gg = fmaf(a, xr * ycv[e], a);
       if (kMask) gg = idv[e] == my_id ? 0.f : gg;
       if (kDiag) gg = (j == diag_j) ? diag_val_scaled : gg;
@@ -437,10 +451,15 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
             const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
             GBW(0, gb_wait(smem_u32(&bars->empty[st]), par ^ 1));
             if (elect_one()) {
+#ifdef GB_DIAG_HALF_Y
+              mbar_expect_tx(smem_u32(&bars->full[st]), P_BOX_BYTES);
+              tma_load_2d(ring + st * GB_STAGE_BYTES, &map_y_k, smem_u32(&bars->full[st]), kb * 64, col * 128);
+#else
               mbar_expect_tx(smem_u32(&bars->full[st]), nkb * P_BOX_BYTES);
               for (int q = 0; q < nkb; ++q)
                 tma_load_2d(ring + st * GB_STAGE_BYTES + q * P_BOX_BYTES, &map_y_k,
                             smem_u32(&bars->full[st]), (kb + q) * 64, col * 128);
+#endif
             }
             __syncwarp();
           }
@@ -448,50 +467,56 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
       }
     } else if (warp == GB_MMA_WARP) {
       const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_K, 128, 128);
-      uint32_t it = 0, tile_ctr = 0, item_ctr = 0, peek = 0;
-      ProdIter items(S, a);
-      VRow vr;
-      int t_base;
-      for (; items.next(vr, t_base); ++item_ctr) {
-        const SchedPhase& ph = items.phase();
-        GBW(1, gb_wait(smem_u32(&bars->x_ready), item_ctr & 1));
-        tc_fence_after();
-        for (int u = 0; u < ph.cs; ++u) {
-          if (sched_col(ph, vr, a, u) < 0) continue;
-          const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
-          const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-          GBW(2, gb_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1));
+      // lean issue path: running stage / parity counters, descriptor words advanced by adds
+      const uint32_t b_hi = sdesc_hi_sw128(1024);
+      const uint32_t b_lo0 = sdesc_lo_sw128(ring, 0);
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      // ONE elected thread runs the whole issue loop (no per-stage elect / reconvergence)
+      if (elect_one()) {
+        uint32_t st = 0, par = 0, tile_ctr = 0, item_ctr = 0, peek = 0;
+        ProdIter items(S, a);
+        VRow vr;
+        int t_base;
+        for (; items.next(vr, t_base); ++item_ctr) {
+          const SchedPhase& ph = items.phase();
+          GBW(1, gb_wait(smem_u32(&bars->x_ready), item_ctr & 1));
           tc_fence_after();
-          const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
-          for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE, ++it) {
-            const uint32_t st = it % GB_P_STAGES, par = (it / GB_P_STAGES) & 1;
-            const int nkb = min(P_KB_PER_STAGE, p.kblocks - kb);
-            if (!peek) GBW(3, gb_wait(smem_u32(&bars->full[st]), par));
+          for (int u = 0; u < ph.cs; ++u) {
+            if (sched_col(ph, vr, a, u) < 0) continue;
+            const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+            const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+            GBW(2, gb_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1));
             tc_fence_after();
-            {   // has the NEXT ring stage landed already?  (answer arrives while the MMAs below issue)
-              const uint32_t nst = (it + 1) % GB_P_STAGES, npar = ((it + 1) / GB_P_STAGES) & 1;
-              peek = mbar_test_wait(smem_u32(&bars->full[nst]), npar);
+            const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
+#ifdef VLP_PROFILE_WAITS
+            const long long ti0 = clock64();
+#endif
+            for (int kb = 0; kb < p.kblocks; kb += P_KB_PER_STAGE) {
+              if (!peek) GBW(3, gb_wait(full0 + st * 8, par));
+              const uint32_t nst = st + 1 == GB_P_STAGES ? 0u : st + 1;
+              const uint32_t npar = nst == 0 ? par ^ 1u : par;
+              const uint32_t lo = b_lo0 + st * (GB_STAGE_BYTES >> 4);
+              const uint32_t at = tmem + BWD_TMEM_X + kb * 32;
+              if (p.kblocks - kb >= 2)
+                peek = umma_ts_stage_peek<8>(d_tmem, at, lo, b_hi, idesc, kb != 0, empty0 + st * 8,
+                                             full0 + nst * 8, npar);
+              else
+                peek = umma_ts_stage_peek<4>(d_tmem, at, lo, b_hi, idesc, kb != 0, empty0 + st * 8,
+                                             full0 + nst * 8, npar);
+              st = nst;
+              par = npar;
             }
-            if (elect_one()) {
-              for (int q = 0; q < nkb; ++q) {
-                const uint32_t sb = ring + st * GB_STAGE_BYTES + q * P_BOX_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_ts<1>(d_tmem, tmem + BWD_TMEM_X + (kb + q) * 32 + ks * 8,
-                             make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | q | ks) != 0);
-              }
-              umma_commit<1>(smem_u32(&bars->empty[st]));
-            }
-            __syncwarp();
+#ifdef VLP_PROFILE_WAITS
+            gbw[14] += clock64() - ti0;
+#endif
+            umma_commit<1>(smem_u32(&bars->s_full[buf]));
+            ++tile_ctr;
           }
-          if (elect_one()) umma_commit<1>(smem_u32(&bars->s_full[buf]));
-          __syncwarp();
-          ++tile_ctr;
+          umma_commit<1>(smem_u32(&bars->x_free));
         }
-        if (elect_one()) umma_commit<1>(smem_u32(&bars->x_free));
-        __syncwarp();
+        if (item_ctr > 0) gb_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
       }
-      if (item_ctr > 0) gb_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+      __syncwarp();
     } else if (warp < GB_SMX_WARPS) {
       // ---- softmax warps: thread = (row, 32-column group) ----
       const uint32_t quarter = warp & 3;
@@ -543,22 +568,43 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
         const int dcol = row_ok ? row - p.diag_shift : -1000000000;
         const int my_id = (P.xid != nullptr && row_ok) ? __ldg(P.xid + row) : -1;
         float ds_acc = 0.f;
+#ifdef GB_DIAG_SMX_DETAIL
+        long long t_end = 0;
+#endif
 
         for (int u = 0; u < ph.cs; ++u) {
           const int col = sched_col(ph, vr, a, u);
           if (col < 0) continue;
           const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
           const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+#ifdef GB_DIAG_SMX_DETAIL
+          const long long tA = clock64();
+          if (t_end != 0) gbw[9] += tA - t_end;
+#endif
           GBW(4, gb_wait(smem_u32(&bars->s_full[buf]), use & 1));
           tc_fence_after();
+#ifdef VLP_PROFILE_WAITS
+          const long long ts0 = clock64();
+#endif
+#ifdef GB_DIAG_SMX_DETAIL
+          gbw[8] += ts0 - tA;
+#endif
           uint32_t v[GB_SMX_COLS];
+#ifdef GB_DIAG_NO_TLD
+#pragma unroll
+          for (int j = 0; j < GB_SMX_COLS; ++j) v[j] = __float_as_uint(xmax) + j + tile_ctr;
+#else
           tmem_ld_x32(tmem + lane_addr + tmem_s_col + buf * 128 + grp * GB_SMX_COLS, v);
           tmem_ld_wait();
+#endif
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->s_empty[buf]));
 
           const int col0 = col * 128 + grp * GB_SMX_COLS;
+#ifdef VLP_PROFILE_WAITS
+          const long long ts1 = clock64();
+#endif
           uint32_t out[GB_SMX_COLS / 2];
           const int diag_j = dcol - col0;
           const bool has_diag = diag_j >= 0 && diag_j < GB_SMX_COLS;
@@ -568,6 +614,12 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
           // (the padded statistics give P = 0 beyond n_cols; the caption ids are padded to whole tiles)
           const bool masked = P.yid != nullptr;
           const int* yid = masked ? P.yid + col0 : nullptr;
+#ifdef GB_DIAG_NO_MATH
+          if (true) {
+#pragma unroll
+            for (int j = 0; j < GB_SMX_COLS / 2; ++j) out[j] = v[2 * j] ^ v[2 * j + 1];
+          } else
+#endif
           if (fast) {
             const float4* yc4 = reinterpret_cast<const float4*>(p.yc + col0);
             float acc = 0.f;
@@ -605,6 +657,13 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
             }
           }
 
+#ifdef VLP_PROFILE_WAITS
+#pragma unroll
+          for (int i_ = 0; i_ < GB_SMX_COLS / 2; ++i_) asm volatile("" ::"r"(out[i_]));
+          gbw[5] += ts1 - ts0;
+          const long long ts2 = clock64();
+          gbw[13] += ts2 - ts1;
+#endif
           // stage the fp16 G tile (K-major, 128B swizzle): the store warp must have read the slot's
           // previous tile
           const uint32_t slot = tile_ctr & 1;
@@ -612,6 +671,14 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
           const uint32_t dst = gslots + slot * G_SLOT_BYTES + ((grp * GB_SMX_COLS) >> 6) * 16384 +
                                row_in_blk * 128;
           const uint32_t cb = ((grp * GB_SMX_COLS) & 63) >> 3;
+#ifdef GB_DIAG_NO_STS
+          {   // keep the values alive with ONE store per thread
+            uint32_t x = 0;
+#pragma unroll
+            for (int c = 0; c < GB_SMX_COLS / 2; ++c) x ^= out[c];
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + ((cb ^ sw) << 4)), "r"(x) : "memory");
+          }
+#else
 #pragma unroll
           for (int c = 0; c < GB_SMX_COLS / 8; ++c) {
             const uint32_t sa = dst + (((cb + c) ^ sw) << 4);
@@ -619,9 +686,25 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
                          "r"(out[c * 4 + 1]), "r"(out[c * 4 + 2]), "r"(out[c * 4 + 3])
                          : "memory");
           }
-          fence_proxy_async_smem();
+#endif
+#ifdef VLP_PROFILE_WAITS
+          const long long ts3 = clock64();
+#endif
+#ifdef GB_DIAG_SMX_DETAIL
+          gbw[10] += ts3 - ts2;
+#endif
+          // (the generic -> async proxy fence for the staged tile is executed once, by the store warp,
+          // behind its acquire of g_staged: 16 fences here cost ~180 cycles of every tile)
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->g_staged[slot]));
+#ifdef VLP_PROFILE_WAITS
+#ifdef GB_DIAG_SMX_DETAIL
+          t_end = clock64();
+          gbw[7] += t_end - ts3;
+#else
+          gbw[7] += clock64() - ts3;
+#endif
+#endif
           ++tile_ctr;
         }
 #pragma unroll
@@ -666,8 +749,11 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
               if (!(pf_rs == rs && pf_t >= last + 1)) GBW(9, gb_poll_ge(done_t + rs * GB_FLAG_STRIDE, last + 1));
             }
             ring_last[rs] = t;
+            fence_proxy_async_smem();   // the softmax warps' st.shared (acquired above) -> async proxy
+#ifndef GB_DIAG_NO_BULK
             bulk_store_1d(P.gring + (((size_t)a * GB_RING_DEPTH + rs) << 15),
                           gslots + slot * G_SLOT_BYTES, G_SLOT_BYTES);
+#endif
             tma_store_commit();
             pf_rs = (rs + 2) % GB_RING_DEPTH;        // flags of the ring slot this warp uses next
             pf_i = ld_acquire_gpu(done_i + pf_rs * GB_FLAG_STRIDE);
@@ -732,58 +818,52 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
         }
       }
     } else if (warp == GB_MMA_WARP) {
-      uint32_t it = 0, tile_ctr = 0, item_ctr = 0, peek = 0;
-      ProdIter items(S, a);
-      VRow vr;
-      int t_base;
-      for (; items.next(vr, t_base); ++item_ctr) {
-        const SchedPhase& ph = items.phase();
-        if (item_ctr > 0) {
-          GBW(3, gb_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1));
-          tc_fence_after();
-        }
-        bool first = true;
-        for (int u = 0; u < ph.cs; ++u) {
-          if (sched_col(ph, vr, a, u) < 0) continue;
-          const int t = t_base + u;
-          const uint32_t slot = tile_ctr & 1;
-          GBW(4, gb_wait(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
-          tc_fence_after();
-          if (lane == 0)   // the tile sits in shared memory: this reader is done with the ring slot
-            st_relaxed_gpu(P.done_i + ((size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH)) * GB_FLAG_STRIDE, t + 1);
-          const uint32_t ga = gslots + slot * G_SLOT_BYTES;
-          for (int nc = 0; nc < n_nc; ++nc) {
-            const int nb = min(4, p.ndb - nc * 4);
-            const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
-            for (int kh = 0; kh < 2; ++kh, ++it) {
-              const uint32_t st = it % GB_C_STAGES, par = (it / GB_C_STAGES) & 1;
-              if (!peek) GBW(5, gb_wait(smem_u32(&bars->full[st]), par));
-              tc_fence_after();
-              {
-                const uint32_t nst = (it + 1) % GB_C_STAGES, npar = ((it + 1) / GB_C_STAGES) & 1;
-                peek = mbar_test_wait(smem_u32(&bars->full[nst]), npar);
-              }
-              if (elect_one()) {
-                const uint32_t sb = ring + st * GB_STAGE_BYTES;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint64_t ad = make_sdesc_sw128(ga + kh * 16384 + i * 32, 0, 1024);
-                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, 8192, 1024);
-                  umma_ss<1>(tmem + nc * 256, ad, bd, idesc, !(first && kh == 0 && i == 0));
-                }
-                umma_commit<1>(smem_u32(&bars->empty[st]));
-              }
-              __syncwarp();
-            }
+      // lean issue path: descriptor words advanced by adds (A = G K-major, B = T MN-major)
+      const uint32_t d_hi = sdesc_hi_sw128(1024);
+      const uint32_t a_lo0 = sdesc_lo_sw128(gslots, 0), b_lo0 = sdesc_lo_sw128(ring, 8192);
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      if (elect_one()) {
+        uint32_t st = 0, par = 0, tile_ctr = 0, item_ctr = 0, peek = 0;
+        ProdIter items(S, a);
+        VRow vr;
+        int t_base;
+        for (; items.next(vr, t_base); ++item_ctr) {
+          const SchedPhase& ph = items.phase();
+          if (item_ctr > 0) {
+            GBW(3, gb_wait(smem_u32(&bars->acc_free), (item_ctr - 1) & 1));
+            tc_fence_after();
           }
-          if (elect_one()) umma_commit<1>(smem_u32(&bars->g_empty[slot]));
-          __syncwarp();
-          first = false;
-          ++tile_ctr;
+          bool first = true;
+          for (int u = 0; u < ph.cs; ++u) {
+            if (sched_col(ph, vr, a, u) < 0) continue;
+            const int t = t_base + u;
+            const uint32_t slot = tile_ctr & 1;
+            GBW(4, gb_wait(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
+            // the tile sits in shared memory: this reader is done with the ring slot
+            st_relaxed_gpu(P.done_i + ((size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH)) * GB_FLAG_STRIDE, t + 1);
+            for (int nc = 0; nc < n_nc; ++nc) {
+              const int nb = min(4, p.ndb - nc * 4);
+              const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_K, MAJOR_MN, 128, nb * 64);
+              for (int kh = 0; kh < 2; ++kh) {
+                if (!peek) GBW(5, gb_wait(full0 + st * 8, par));
+                const uint32_t nst = st + 1 == GB_C_STAGES ? 0u : st + 1;
+                const uint32_t npar = nst == 0 ? par ^ 1u : par;
+                const uint32_t a_lo = a_lo0 + slot * (G_SLOT_BYTES >> 4) + kh * (16384 >> 4);
+                const uint32_t b_lo = b_lo0 + st * (GB_STAGE_BYTES >> 4);
+                peek = umma_ss_stage4_peek(tmem + nc * 256, a_lo, 2u, b_lo, d_hi, idesc,
+                                           (uint32_t)!(first && kh == 0), empty0 + st * 8, full0 + nst * 8, npar);
+                st = nst;
+                par = npar;
+              }
+            }
+            umma_commit<1>(smem_u32(&bars->g_empty[slot]));
+            first = false;
+            ++tile_ctr;
+          }
+          umma_commit<1>(smem_u32(&bars->acc_full));
         }
-        if (elect_one()) umma_commit<1>(smem_u32(&bars->acc_full));
-        __syncwarp();
       }
+      __syncwarp();
     } else if (warp < GB_EPI_WARPS) {
       const uint32_t quarter = warp & 3;
       const uint32_t lane_addr = (quarter * 32u) << 16;
@@ -869,53 +949,47 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
         }
       }
     } else if (warp == GB_MMA_WARP) {
-      uint32_t it = 0, tile_ctr = 0, piece_ctr = 0, peek = 0;
-      PieceIter pieces(S, q);
-      Piece pc;
-      for (; pieces.next(pc); ++piece_ctr) {
-        if (piece_ctr > 0) {
-          GBW(3, gb_wait(smem_u32(&bars->acc_free), (piece_ctr - 1) & 1));
-          tc_fence_after();
-        }
-        for (int a = pc.a_hi; a >= pc.a_lo; --a, ++tile_ctr) {
-          const int t = pc.t_hi + (pc.a_hi - a);
-          const uint32_t slot = tile_ctr & 1;
-          GBW(4, gb_wait(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
-          tc_fence_after();
-          if (lane == 0)
-            st_relaxed_gpu(P.done_t + ((size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH)) * GB_FLAG_STRIDE, t + 1);
-          const uint32_t ga = gslots + slot * G_SLOT_BYTES;
-          for (int nc = 0; nc < n_nc; ++nc) {
-            const int nb = min(4, p.ndb - nc * 4);
-            // A = G^T: the K-major tile the producer staged, read MN-major (M = column j, K = row i)
-            const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_MN, MAJOR_MN, 128, nb * 64);
-            for (int kh = 0; kh < 2; ++kh, ++it) {
-              const uint32_t st = it % GB_C_STAGES, par = (it / GB_C_STAGES) & 1;
-              if (!peek) GBW(5, gb_wait(smem_u32(&bars->full[st]), par));
-              tc_fence_after();
-              {
-                const uint32_t nst = (it + 1) % GB_C_STAGES, npar = ((it + 1) / GB_C_STAGES) & 1;
-                peek = mbar_test_wait(smem_u32(&bars->full[nst]), npar);
-              }
-              if (elect_one()) {
-                const uint32_t sb = ring + st * GB_STAGE_BYTES;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint64_t ad = make_sdesc_sw128(ga + (kh * 4 + i) * 2048, 16384, 1024);
-                  const uint64_t bd = make_sdesc_sw128(sb + i * 2048, 8192, 1024);
-                  umma_ss<1>(tmem + nc * 256, ad, bd, idesc, !(a == pc.a_hi && kh == 0 && i == 0));
-                }
-                umma_commit<1>(smem_u32(&bars->empty[st]));
-              }
-              __syncwarp();
-            }
+      // lean issue path (A = G^T: the K-major image read MN-major, LBO 16 KB; B = I MN-major)
+      const uint32_t d_hi = sdesc_hi_sw128(1024);
+      const uint32_t a_lo0 = sdesc_lo_sw128(gslots, 16384), b_lo0 = sdesc_lo_sw128(ring, 8192);
+      const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+      if (elect_one()) {
+        uint32_t st = 0, par = 0, tile_ctr = 0, piece_ctr = 0, peek = 0;
+        PieceIter pieces(S, q);
+        Piece pc;
+        for (; pieces.next(pc); ++piece_ctr) {
+          if (piece_ctr > 0) {
+            GBW(3, gb_wait(smem_u32(&bars->acc_free), (piece_ctr - 1) & 1));
+            tc_fence_after();
           }
-          if (elect_one()) umma_commit<1>(smem_u32(&bars->g_empty[slot]));
-          __syncwarp();
+          for (int a = pc.a_hi; a >= pc.a_lo; --a, ++tile_ctr) {
+            const int t = pc.t_hi + (pc.a_hi - a);
+            const uint32_t slot = tile_ctr & 1;
+            GBW(4, gb_wait(smem_u32(&bars->g_full[slot]), (tile_ctr >> 1) & 1));
+            st_relaxed_gpu(P.done_t + ((size_t)a * GB_RING_DEPTH + (t % GB_RING_DEPTH)) * GB_FLAG_STRIDE, t + 1);
+            for (int nc = 0; nc < n_nc; ++nc) {
+              const int nb = min(4, p.ndb - nc * 4);
+              // A = G^T: the K-major tile the producer staged, read MN-major (M = column j, K = row i)
+              const uint32_t idesc = make_idesc(UMMA_F16, UMMA_F16, MAJOR_MN, MAJOR_MN, 128, nb * 64);
+              for (int kh = 0; kh < 2; ++kh) {
+                if (!peek) GBW(5, gb_wait(full0 + st * 8, par));
+                const uint32_t nst = st + 1 == GB_C_STAGES ? 0u : st + 1;
+                const uint32_t npar = nst == 0 ? par ^ 1u : par;
+                const uint32_t a_lo = a_lo0 + slot * (G_SLOT_BYTES >> 4) + kh * (4 * 2048 >> 4);
+                const uint32_t b_lo = b_lo0 + st * (GB_STAGE_BYTES >> 4);
+                peek = umma_ss_stage4_peek(tmem + nc * 256, a_lo, 128u, b_lo, d_hi, idesc,
+                                           (uint32_t)!(a == pc.a_hi && kh == 0), empty0 + st * 8,
+                                           full0 + nst * 8, npar);
+                st = nst;
+                par = npar;
+              }
+            }
+            umma_commit<1>(smem_u32(&bars->g_empty[slot]));
+          }
+          umma_commit<1>(smem_u32(&bars->acc_full));
         }
-        if (elect_one()) umma_commit<1>(smem_u32(&bars->acc_full));
-        __syncwarp();
       }
+      __syncwarp();
     } else if (warp < GB_EPI_WARPS) {
       const uint32_t quarter = warp & 3;
       const uint32_t lane_addr = (quarter * 32u) << 16;
@@ -984,7 +1058,13 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
   }
 
 #ifdef VLP_PROFILE_WAITS
-  if (p.wait_prof != nullptr && lane == 0 && (warp == 0 || warp >= GB_STORE_WARP) && warp != GB_STORE_WARP + 1) {
+#ifdef GB_DIAG_SMX_DETAIL
+  const bool prof_skip = blockIdx.x < P.np && warp == GB_STORE_WARP;   // slots 8..10 carry softmax detail
+#else
+  const bool prof_skip = false;
+#endif
+  if (p.wait_prof != nullptr && lane == 0 && (warp == 0 || warp >= GB_STORE_WARP) && warp != GB_STORE_WARP + 1 &&
+      !prof_skip) {
     long long* o = p.wait_prof + (size_t)blockIdx.x * 16;
     for (int i = 0; i < 15; ++i)
       if (gbw[i] != 0) o[i] = gbw[i];

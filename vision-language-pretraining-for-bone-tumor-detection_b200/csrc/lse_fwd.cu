@@ -168,50 +168,49 @@ lse_partial_kernel(const __grid_constant__ CUtensorMap map_y, const LseParams p)
     // ================= MMA issuer (whole warp converged, one elected lane issues) ===========
     const uint32_t fmt = p.operand_f16 ? UMMA_F16 : UMMA_BF16;
     const uint32_t idesc = make_idesc(fmt, fmt, MAJOR_K, MAJOR_K, 128, 128);
-    uint32_t it = 0, tile_ctr = 0, item_ctr = 0, peek = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
-      const int chunk = item / p.n_row_blocks;
-      const int t0 = chunk * p.tiles_per_chunk;
-      const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-      mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
-      tc_fence_after();
-      for (int q = 0; q < kLead + t1 - t0; ++q, ++tile_ctr) {
-        const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
-        const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-        mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1);
+    // lean issue path (see sm100_ptx.cuh): running stage / parity counters, descriptor words advanced by adds
+    static_assert(FWD_KB_PER_STAGE == 2 && FWD_BOX_BYTES == 16384, "umma_ts_stage layout");
+    const uint32_t b_hi = sdesc_hi_sw128(1024);
+    const uint32_t b_lo0 = sdesc_lo_sw128(ring, 0);
+    const uint32_t full0 = smem_u32(&bars->full[0]), empty0 = smem_u32(&bars->empty[0]);
+    // ONE elected thread runs the whole issue loop (no per-stage elect / reconvergence)
+    if (elect_one()) {
+      uint32_t st = 0, par = 0, tile_ctr = 0, item_ctr = 0, peek = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
+        const int chunk = item / p.n_row_blocks;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        mbar_wait(smem_u32(&bars->x_ready), item_ctr & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
-        for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE, ++it) {
-          const uint32_t st = it % FWD_STAGES;
-          const uint32_t ph = (it / FWD_STAGES) & 1;
-          const int nkb = min(FWD_KB_PER_STAGE, p.kblocks - kb);
-          if (!peek) mbar_wait(smem_u32(&bars->full[st]), ph);
+        for (int q = 0; q < kLead + t1 - t0; ++q, ++tile_ctr) {
+          const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
+          const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
+          mbar_wait(smem_u32(&bars->s_empty[buf]), (use & 1) ^ 1);
           tc_fence_after();
-          {   // has the NEXT ring stage landed already?  (answer arrives while the MMAs below issue)
-            const uint32_t nst = (it + 1) % FWD_STAGES, nph = ((it + 1) / FWD_STAGES) & 1;
-            peek = mbar_test_wait(smem_u32(&bars->full[nst]), nph);
+          const uint32_t d_tmem = tmem + tmem_s_col + buf * 128;
+          for (int kb = 0; kb < p.kblocks; kb += FWD_KB_PER_STAGE) {
+            if (!peek) mbar_wait(full0 + st * 8, par);
+            const uint32_t nst = st + 1 == FWD_STAGES ? 0u : st + 1;
+            const uint32_t npar = nst == 0 ? par ^ 1u : par;
+            const uint32_t lo = b_lo0 + st * (FWD_STAGE_BYTES >> 4);
+            const uint32_t at = tmem + TMEM_X_COL + kb * 32;
+            if (p.kblocks - kb >= 2)
+              peek = umma_ts_stage_peek<8>(d_tmem, at, lo, b_hi, idesc, kb != 0, empty0 + st * 8,
+                                           full0 + nst * 8, npar);
+            else
+              peek = umma_ts_stage_peek<4>(d_tmem, at, lo, b_hi, idesc, kb != 0, empty0 + st * 8,
+                                           full0 + nst * 8, npar);
+            st = nst;
+            par = npar;
           }
-          if (elect_one()) {
-            for (int q = 0; q < nkb; ++q) {
-              const uint32_t sb = ring + st * FWD_STAGE_BYTES + q * FWD_BOX_BYTES;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                umma_ts<1>(d_tmem, tmem + TMEM_X_COL + (kb + q) * 32 + ks * 8,
-                           make_sdesc_sw128(sb + ks * 32, 0, 1024), idesc, (kb | q | ks) != 0);
-              }
-            }
-            umma_commit<1>(smem_u32(&bars->empty[st]));
-          }
-          __syncwarp();
+          umma_commit<1>(smem_u32(&bars->s_full[buf]));
         }
-        if (elect_one()) umma_commit<1>(smem_u32(&bars->s_full[buf]));
-        __syncwarp();
+        umma_commit<1>(smem_u32(&bars->x_free));
       }
-      if (elect_one()) umma_commit<1>(smem_u32(&bars->x_free));
-      __syncwarp();
+      // do not exit with an arrive still in flight
+      if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
     }
-    // do not exit with an arrive still in flight
-    if (item_ctr > 0) mbar_wait(smem_u32(&bars->x_free), (item_ctr - 1) & 1);
+    __syncwarp();
   } else {
     // ================= softmax warps =================
     // thread = (row, column group): quarter = TMEM lane quarter of the warp, cg = 32-column group

@@ -326,6 +326,18 @@ VLP_DEVICE uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uin
   return d;
 }
 
+// The two 32-bit words of a descriptor.  The high word (SBO, version, swizzle) is loop invariant and an
+// smem offset only moves the low word's 14-bit address field ((addr & 0x3FFFF) >> 4 never carries out
+// of it for a valid address), so an issue loop needs ONE 32-bit add per MMA instead of rebuilding the
+// 64-bit descriptor (the MMA warp's issue path is a dependent chain of uniform-datapath instructions:
+// its length, not the tensor pipe, bounded the S-tile kernels -- profiles/r02_issue_path.txt).
+VLP_DEVICE uint32_t sdesc_lo_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+VLP_DEVICE uint32_t sdesc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05: MMA + commit
 // ----------------------------------------------------------------------------
@@ -396,7 +408,187 @@ VLP_DEVICE void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint3
   }
 }
 
+// word-form variants (cta_group::1): descriptors passed as {lo, hi} 32-bit words, accumulate flag as
+// a compile-time-foldable integer
+VLP_DEVICE void umma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 bd;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 bd, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+VLP_DEVICE void umma_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 ad, bd;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 ad, {%1, %2};\n"
+      "mov.b64 bd, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One ring stage of an S tile, TS form: NM MMAs (K = 16 each) over NM / 4 boxes of [128 rows x 64 k]
+// (16 KB apart); A advances 8 TMEM columns per MMA.  Fully unrolled: one add per operand per MMA.
+template <int NM>
+VLP_DEVICE void umma_ts_stage(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                              uint32_t idesc, uint32_t first_accumulate) {
+#pragma unroll
+  for (int j = 0; j < NM; ++j)
+    umma_ts_w(d_tmem, a_tmem + j * 8, b_lo + (j >> 2) * (16384 >> 4) + (j & 3) * 2, b_hi, idesc,
+              j == 0 ? first_accumulate : 1u);
+}
+
 // all previously issued MMAs of this thread arrive (once) on `bar` when they complete
+
+// One ring stage in ONE asm block: peek at the NEXT stage's "full" barrier (mbarrier.test_wait, ~100
+// cycles of latency), issue this stage's MMAs, commit them to this stage's "empty" barrier, and only
+// then read the peek's answer -- so the barrier latency hides under the issue.  Returns 1 when the
+// next stage had landed.  Meant for a single elected thread that runs the whole issue loop.
+template <int NM>
+VLP_DEVICE uint32_t umma_ts_stage_peek(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                       uint32_t idesc, uint32_t first_accumulate, uint32_t commit_bar,
+                                       uint32_t peek_bar, uint32_t peek_parity);
+template <>
+VLP_DEVICE uint32_t umma_ts_stage_peek<8>(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t first_accumulate, uint32_t commit_bar,
+                                             uint32_t peek_bar, uint32_t peek_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pt, q;\n"
+      ".reg .b64 bd;\n"
+      ".reg .b32 ta, lo;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 q, [%8], %9;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.ne.b32 pt, %10, 0;\n"
+      "mov.b64 bd, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], bd, %5, p;\n"
+      "add.u32 ta, %2, 8;\n"
+      "add.u32 lo, %3, 2;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "add.u32 ta, %2, 16;\n"
+      "add.u32 lo, %3, 4;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "add.u32 ta, %2, 24;\n"
+      "add.u32 lo, %3, 6;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "add.u32 ta, %2, 32;\n"
+      "add.u32 lo, %3, 1024;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "add.u32 ta, %2, 40;\n"
+      "add.u32 lo, %3, 1026;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "add.u32 ta, %2, 48;\n"
+      "add.u32 lo, %3, 1028;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "add.u32 ta, %2, 56;\n"
+      "add.u32 lo, %3, 1030;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
+      "selp.u32 %0, 1, 0, q;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(first_accumulate), "r"(commit_bar),
+        "r"(peek_bar), "r"(peek_parity), "r"(1u)
+      : "memory");
+  return ok;
+}
+template <>
+VLP_DEVICE uint32_t umma_ts_stage_peek<4>(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t first_accumulate, uint32_t commit_bar,
+                                             uint32_t peek_bar, uint32_t peek_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pt, q;\n"
+      ".reg .b64 bd;\n"
+      ".reg .b32 ta, lo;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 q, [%8], %9;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.ne.b32 pt, %10, 0;\n"
+      "mov.b64 bd, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], bd, %5, p;\n"
+      "add.u32 ta, %2, 8;\n"
+      "add.u32 lo, %3, 2;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "add.u32 ta, %2, 16;\n"
+      "add.u32 lo, %3, 4;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "add.u32 ta, %2, 24;\n"
+      "add.u32 lo, %3, 6;\n"
+      "mov.b64 bd, {lo, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], [ta], bd, %5, pt;\n"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n"
+      "selp.u32 %0, 1, 0, q;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(first_accumulate), "r"(commit_bar),
+        "r"(peek_bar), "r"(peek_parity), "r"(1u)
+      : "memory");
+  return ok;
+}
+// ... SS form, 4 MMAs of one consumer stage: A low word advances by a_step per MMA, B by 128 (2 KB)
+VLP_DEVICE uint32_t umma_ss_stage4_peek(uint32_t d_tmem, uint32_t a_lo, uint32_t a_step, uint32_t b_lo,
+                                        uint32_t d_hi, uint32_t idesc, uint32_t first_accumulate,
+                                        uint32_t commit_bar, uint32_t peek_bar, uint32_t peek_parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pt, q;\n"
+      ".reg .b64 ad, bd;\n"
+      ".reg .b32 la, lb;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 q, [%9], %10;\n"
+      "setp.ne.b32 p, %7, 0;\n"
+      "setp.ne.b32 pt, %11, 0;\n"
+      "mov.b64 ad, {%2, %5};\n"
+      "mov.b64 bd, {%4, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], ad, bd, %6, p;\n"
+      "mad.lo.u32 la, %3, 1, %2;\n"
+      "add.u32 lb, %4, 128;\n"
+      "mov.b64 ad, {la, %5};\n"
+      "mov.b64 bd, {lb, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], ad, bd, %6, pt;\n"
+      "mad.lo.u32 la, %3, 2, %2;\n"
+      "add.u32 lb, %4, 256;\n"
+      "mov.b64 ad, {la, %5};\n"
+      "mov.b64 bd, {lb, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], ad, bd, %6, pt;\n"
+      "mad.lo.u32 la, %3, 3, %2;\n"
+      "add.u32 lb, %4, 384;\n"
+      "mov.b64 ad, {la, %5};\n"
+      "mov.b64 bd, {lb, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], ad, bd, %6, pt;\n"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n"
+      "selp.u32 %0, 1, 0, q;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(d_tmem), "r"(a_lo), "r"(a_step), "r"(b_lo), "r"(d_hi), "r"(idesc), "r"(first_accumulate),
+        "r"(commit_bar), "r"(peek_bar), "r"(peek_parity), "r"(1u)
+      : "memory");
+  return ok;
+}
+
 template <int CTA_GROUP>
 VLP_DEVICE void umma_commit(uint32_t bar) {
   if constexpr (CTA_GROUP == 1) {
