@@ -416,10 +416,16 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for w in range(max(3, args.warmup)):
-        step(*sets[w % 2])
+    # the warm-up runs exactly like the timed loop (same live tensors, same 2-step run-ahead), so that
+    # the caching allocator has reached its steady state: a warm-up that drops the returned gradients
+    # leaves a cudaMalloc of 2 x 64 MB for the second timed step (seen as one 5-11 ms step)
+    wmarks = []
+    for w in range(max(4, args.warmup)):
+        loss, dI_last, dT_last = step(*sets[w % 2])
+        wmarks.append(torch.cuda.Event())
+        wmarks[-1].record()
         if w >= 2:
-            torch.cuda.synchronize()
+            wmarks[w - 2].synchronize()
     sync_all()
     sampler.active = True
     launches0 = lib.vlpclip_launch_count() + VF.GRAPH_REPLAYED_LAUNCHES
@@ -433,13 +439,16 @@ def run_ours(args):
     e0.record()
     for k in range(args.steps):
         loss, dI_last, dT_last = step(*sets[k % 2])
-        marks.append(torch.cuda.Event())
+        marks.append(torch.cuda.Event(enable_timing=True))
         marks[-1].record()
         if k >= 2:
             marks[k - 2].synchronize()
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+    if os.environ.get("VLP_BENCH_STEP_TIMES"):   # dev: per-step device times of the timed region
+        ts = [e0.elapsed_time(marks[0])] + [marks[i - 1].elapsed_time(marks[i]) for i in range(1, len(marks))]
+        print("step ms:", " ".join(f"{t:.2f}" for t in ts), file=sys.stderr)
     last_set = (args.steps - 1) % 2
     dls_last = ls.grad.detach().clone()
     sampler.active = False

@@ -273,10 +273,13 @@ int vlpclip_project_normalize_fwd(const float* feat, const float* w, int n, int 
 int vlpclip_normalize_bwd(const float* emb_f32, const float* d_emb, const float* inv_norm, int n,
                           int d, float* du, void* stream);
 
-/* generic small GEMMs of the projection backward (tf32 tensor cores, fp32 accumulate):
+/* generic small GEMMs of the projection and its backward (tf32 tensor cores, fp32 accumulate):
  *   C[m, n] = A[m, k] @ B[k, n]      (trans_a = 0)
  *   C[m, n] = A[k, m]^T @ B[k, n]    (trans_a = 1)   -- dW = feat^T du
  *   trans_b = 1 reads B as [n, k]                    -- dfeat = du W^T
+ * All operands row-major fp32 and read in place (no transposed copies); the contiguous extent of
+ * each operand must be a multiple of 4 floats.  The workspace only holds split-K partial sums
+ * (summed in a fixed order: results are bit-reproducible).
  */
 int vlpclip_gemm_tf32(const float* a, const float* b, float* c, int m, int n, int k, int trans_a,
                       int trans_b, void* workspace, size_t workspace_bytes, void* stream);

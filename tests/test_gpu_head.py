@@ -162,3 +162,28 @@ def test_module_training_step_end_to_end():
     m.validation_step(batch, 0, dataloader_idx=0)
     m.on_validation_epoch_end()
     assert "val/combined/loss" in getattr(m, "logged", {"val/combined/loss": 1})
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 312, 512), (1000, 512, 312), (512, 512, 4100), (37, 72, 100),
+                                   (312, 512, 3001)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_tf32_all_operand_majors(m, n, k, ta, tb):
+    """vlpclip_gemm_tf32 reads row-major operands in either orientation without copying them (K-major or
+    MN-major UMMA descriptors); against an fp64 product, tolerance = tf32 operand rounding (2^-11)."""
+    from vlp_b200 import functional as VF
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(m * 7 + n * 3 + k + ta * 2 + tb)
+    a = torch.randn((k, m) if ta else (m, k), generator=g, device=dev)
+    b = torch.randn((n, k) if tb else (k, n), generator=g, device=dev)
+    # the contiguous extent of each operand must be a multiple of 4 floats
+    if (a.shape[1] % 4) or (b.shape[1] % 4):
+        with pytest.raises((RuntimeError, ValueError)):
+            VF._gemm_tf32(a, b, m, n, k, ta, tb)
+        return
+    c = VF._gemm_tf32(a, b, m, n, k, ta, tb)
+    torch.cuda.synchronize()
+    ref = (a.double().T if ta else a.double()) @ (b.double().T if tb else b.double())
+    err = ((c.double() - ref).norm() / ref.norm()).item()
+    assert err < 1.5e-3, err
+    c2 = VF._gemm_tf32(a, b, m, n, k, ta, tb)
+    assert torch.equal(c, c2)          # split-K partials are summed in a fixed order

@@ -51,8 +51,11 @@ inline EncodeTiledFn get_encode_fn() {
 
 // Row-major [outer][inner] matrix of `elem_bytes`-wide elements, row stride `ld` elements.
 // Box = {128 B worth of inner elements, box_outer rows}, 128-byte swizzle, OOB reads give 0.
+// atom32: the 128B swizzle moves 32-byte chunks (XOR with row mod 4) instead of 16-byte ones -- the only
+// shared-memory layout the tensor cores accept for MN-major 32-bit (tf32) operands.
 inline int make_tmap_sw128(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner,
-                           uint64_t outer, uint64_t ld, uint32_t box_outer, bool as_float32 = false) {
+                           uint64_t outer, uint64_t ld, uint32_t box_outer, bool as_float32 = false,
+                           bool atom32 = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(-3, "cuTensorMapEncodeTiled unavailable (driver too old?)");
   if ((reinterpret_cast<uintptr_t>(gptr) & 15) != 0)
@@ -69,7 +72,8 @@ inline int make_tmap_sw128(CUtensorMap* out, const void* gptr, int elem_bytes, u
                            : as_float32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                            : CU_TENSOR_MAP_DATA_TYPE_UINT32;
   CUresult r = enc(out, dt, 2, const_cast<void*>(gptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-5, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;

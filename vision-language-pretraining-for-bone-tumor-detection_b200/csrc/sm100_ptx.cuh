@@ -337,6 +337,11 @@ VLP_DEVICE uint32_t sdesc_lo_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
 VLP_DEVICE uint32_t sdesc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
+// layout type 1 = 128B swizzle with a 32-byte base (MN-major tf32 operands; atom = 4 k rows of 128 B,
+// SBO = byte stride between 4-row groups)
+VLP_DEVICE uint32_t sdesc_hi_sw128_base32(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (1u << 29);
+}
 
 // ----------------------------------------------------------------------------
 // tcgen05: MMA + commit
@@ -378,6 +383,23 @@ VLP_DEVICE void umma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, 
       "}\n"
       :
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// word-form variant (see umma_ss_w)
+VLP_DEVICE void umma_ss_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 ad, bd;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 ad, {%1, %2};\n"
+      "mov.b64 bd, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %5, p;\n"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 

@@ -1039,6 +1039,7 @@ class _ProjectNormalize(torch.autograd.Function):
         ctx.save_for_backward(f32, w32, emb, inv_norm)
         ctx.in_dtypes = (features.dtype, weight.dtype)
         ctx.mark_non_differentiable(emb_bf16, emb_f16)
+        ctx.set_materialize_grads(False)   # no 2 x 32 MB zero "gradients" for the operand copies
         return emb, emb_bf16, emb_f16
 
     @staticmethod
