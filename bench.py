@@ -56,6 +56,9 @@ def measured_peaks():
 # --------------------------------------------------------------------------------------------
 # clocks
 # --------------------------------------------------------------------------------------------
+PRIMING_STEPS = 3   # untimed steps before the W warm-up steps (see main): allocator steady state
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled every ~10 ms DURING the timed region (NVML in a thread;
     falls back to one `nvidia-smi` query when pynvml is unavailable)."""
@@ -70,7 +73,8 @@ class ClockSampler:
         self.max_mhz = None
         self._stop = False
         self._thread = None
-        self.active = False      # samples are kept only while the timed region runs
+        self.active = False      # polling runs from the warm-up on ...
+        self.timed = False       # ... samples are kept only while the timed region runs
 
     def _run(self):
         import pynvml
@@ -89,11 +93,13 @@ class ClockSampler:
                 time.sleep(0.002)
                 continue
             try:
-                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
+                if self.timed:      # (queries during the warm-up only take the first-call costs of NVML)
+                    self.samples.append(mhz)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.01)
@@ -206,7 +212,8 @@ def workload_config(n, d, world):
             "global_batch": n, "dim": d, "rows_per_gpu": b, "logit_scale": LOGIT_SCALE,
             "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
             "l2": "two input sets rotated; inputs+operand copies+gradients = "
-                  f"{(2 * n * d * 4 + 2 * 2 * n * d * 2 + 2 * n * d * 4) / 1e6:.0f} MB per step > 126 MB L2"}
+                  f"{(2 * n * d * 4 + 2 * 2 * n * d * 2 + 2 * n * d * 4) / 1e6:.0f} MB per step > 126 MB L2",
+            "untimed_steps": f"{PRIMING_STEPS} allocator-priming steps + the W warm-up steps, same loop as the timed K"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -419,15 +426,19 @@ def run_ours(args):
     # the warm-up runs exactly like the timed loop (same live tensors, same 2-step run-ahead), so that
     # the caching allocator has reached its steady state: a warm-up that drops the returned gradients
     # leaves a cudaMalloc of 2 x 64 MB for the second timed step (seen as one 5-11 ms step)
+    # (3 priming steps come before the W warm-up steps: the fourth step of a process is the first one the
+    #  host enqueues two steps ahead of the GPU with every buffer of the pattern alive, and the allocator
+    #  answers it with fresh cudaMallocs -- 5-18 ms when it falls into the timed region, as it did with W = 3)
     wmarks = []
-    for w in range(max(4, args.warmup)):
+    sampler.active = True
+    for w in range(PRIMING_STEPS + max(3, args.warmup)):
         loss, dI_last, dT_last = step(*sets[w % 2])
         wmarks.append(torch.cuda.Event())
         wmarks[-1].record()
         if w >= 2:
             wmarks[w - 2].synchronize()
     sync_all()
-    sampler.active = True
+    sampler.timed = True
     launches0 = lib.vlpclip_launch_count() + VF.GRAPH_REPLAYED_LAUNCHES
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -451,6 +462,7 @@ def run_ours(args):
         print("step ms:", " ".join(f"{t:.2f}" for t in ts), file=sys.stderr)
     last_set = (args.steps - 1) % 2
     dls_last = ls.grad.detach().clone()
+    sampler.timed = False
     sampler.active = False
     launches = lib.vlpclip_launch_count() + VF.GRAPH_REPLAYED_LAUNCHES - launches0
     if world > 1:
@@ -602,7 +614,7 @@ def run_ours(args):
             loss_host.copy_(loss.detach().reshape(1), non_blocking=False)   # D2H read of the result
         return float(loss_host.item())
 
-    e2e_loop(2)
+    e2e_loop(PRIMING_STEPS + 3)
     sync_all()
     t0 = time.perf_counter()
     g0 = torch.cuda.Event(enable_timing=True)
@@ -636,14 +648,25 @@ def run_ours(args):
     f_alg_head = f_alg_step + 6.0 * n * (F_I + F_T) * d
     head_tflops = f_alg_head / (head_ms * 1e-3) / 1e12 / world
     traffic, traffic_source = None, "not measured in this run (ncu is not part of the bench)"
-    prof = os.path.join(ROOT, "profiles", "r02_ncu_grad_both.json")
-    if world == 1 and n == 32768 and d == 512 and os.path.exists(prof):
+    fwd_traffic, fwd_traffic_source = None, traffic_source
+
+    def _ncu_traffic(name):
+        prof = os.path.join(ROOT, "profiles", name)
+        m = json.load(open(prof))["metrics"]
+        return (float(m["dram__bytes_read.sum"]["value"]) + float(m["dram__bytes_write.sum"]["value"])) * 1e6
+
+    if world == 1 and n == 32768 and d == 512:
+        src = "profiles/%s: one ncu --set full capture of this kernel on this workload (committed, not this run)"
         try:
-            m = json.load(open(prof))["metrics"]
-            traffic = (float(m["dram__bytes_read.sum"]["value"]) + float(m["dram__bytes_write.sum"]["value"])) * 1e6
-            traffic_source = "profiles/r02_ncu_grad_both.json: one ncu --set full capture of this kernel on this workload (committed, not this run)"
+            traffic = _ncu_traffic("r02_ncu_grad_both_final.json")
+            traffic_source = src % "r02_ncu_grad_both_final.json"
         except Exception:
             traffic = None
+        try:
+            fwd_traffic = _ncu_traffic("r02_ncu_lse_fwd_final.json")
+            fwd_traffic_source = src % "r02_ncu_lse_fwd_final.json"
+        except Exception:
+            fwd_traffic = None
     cpu = None
     tgb = None
     cfs = None
@@ -668,6 +691,7 @@ def run_ours(args):
                      "frac": grad_tflops / peaks["bf16_tflops"],
                      "frac_of_sustained": grad_tflops / peaks["bf16_tflops_sustained"],
                      "frac_executed": 1.5 * grad_tflops / peaks["bf16_tflops"],
+                     "frac_executed_of_sustained": 1.5 * grad_tflops / peaks["bf16_tflops_sustained"],
                      "peak_source": peaks["source"] + " (burst cuBLAS bf16)",
                      "ms_per_launch": grad_ms, "ms_per_call_with_helpers": grad_call_ms,
                      "algorithmic_flops_per_launch": f_alg_grad,
@@ -678,7 +702,7 @@ def run_ours(args):
                              "frac": fwd_tflops / peaks["bf16_tflops"],
                              "frac_of_sustained": fwd_tflops / peaks["bf16_tflops_sustained"],
                              "ms_per_call": fwd_ms, "algorithmic_flops_per_launch": f_alg_fwd,
-                             "traffic": None, "traffic_source": "not measured in this run"},
+                             "traffic": fwd_traffic, "traffic_source": fwd_traffic_source},
         "full_head": {"what": "projection + L2-normalise prologue (image 512 -> d, text 312 -> d), loss, and the "
                               "whole backward (dW, d features, d logit_scale) inside the CUDA-event bracket",
                       "value": n / (head_ms * 1e-3), "unit": UNIT, "ms_per_step": head_ms,
