@@ -121,6 +121,9 @@ __device__ __forceinline__ void gb_poll_ge(const int* flag, int target) {
 }
 
 // -DVLP_PROFILE_WAITS: cycles each role spends blocked (dev tool; counters per CTA, see tools/check_grad_both.py)
+// -DGB_DIAG_NO_STS / NO_BULK / HALF_Y / NO_TLD / NO_EX2 / NO_MATH: elimination builds (tools/diag_build.sh) that
+// remove one ingredient of the producer tile -- their RESULTS ARE WRONG on purpose, they exist to time the rest
+// (profiles/r02_issue_path.txt).  None of them is defined in the shipped library.
 #ifdef VLP_PROFILE_WAITS
 #define GBW(idx, stmt)                  \
   do {                                  \
@@ -568,26 +571,16 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
         const int dcol = row_ok ? row - p.diag_shift : -1000000000;
         const int my_id = (P.xid != nullptr && row_ok) ? __ldg(P.xid + row) : -1;
         float ds_acc = 0.f;
-#ifdef GB_DIAG_SMX_DETAIL
-        long long t_end = 0;
-#endif
 
         for (int u = 0; u < ph.cs; ++u) {
           const int col = sched_col(ph, vr, a, u);
           if (col < 0) continue;
           const uint32_t buf = nbuf == 2 ? (tile_ctr & 1) : 0;
           const uint32_t use = nbuf == 2 ? (tile_ctr >> 1) : tile_ctr;
-#ifdef GB_DIAG_SMX_DETAIL
-          const long long tA = clock64();
-          if (t_end != 0) gbw[9] += tA - t_end;
-#endif
           GBW(4, gb_wait(smem_u32(&bars->s_full[buf]), use & 1));
           tc_fence_after();
 #ifdef VLP_PROFILE_WAITS
           const long long ts0 = clock64();
-#endif
-#ifdef GB_DIAG_SMX_DETAIL
-          gbw[8] += ts0 - tA;
 #endif
           uint32_t v[GB_SMX_COLS];
 #ifdef GB_DIAG_NO_TLD
@@ -690,20 +683,12 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
 #ifdef VLP_PROFILE_WAITS
           const long long ts3 = clock64();
 #endif
-#ifdef GB_DIAG_SMX_DETAIL
-          gbw[10] += ts3 - ts2;
-#endif
           // (the generic -> async proxy fence for the staged tile is executed once, by the store warp,
           // behind its acquire of g_staged: 16 fences here cost ~180 cycles of every tile)
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->g_staged[slot]));
 #ifdef VLP_PROFILE_WAITS
-#ifdef GB_DIAG_SMX_DETAIL
-          t_end = clock64();
-          gbw[7] += t_end - ts3;
-#else
           gbw[7] += clock64() - ts3;
-#endif
 #endif
           ++tile_ctr;
         }
@@ -1058,13 +1043,7 @@ grad_both_kernel(const __grid_constant__ CUtensorMap map_y_k,   // T: box {64 k,
   }
 
 #ifdef VLP_PROFILE_WAITS
-#ifdef GB_DIAG_SMX_DETAIL
-  const bool prof_skip = blockIdx.x < P.np && warp == GB_STORE_WARP;   // slots 8..10 carry softmax detail
-#else
-  const bool prof_skip = false;
-#endif
-  if (p.wait_prof != nullptr && lane == 0 && (warp == 0 || warp >= GB_STORE_WARP) && warp != GB_STORE_WARP + 1 &&
-      !prof_skip) {
+  if (p.wait_prof != nullptr && lane == 0 && (warp == 0 || warp >= GB_STORE_WARP) && warp != GB_STORE_WARP + 1) {
     long long* o = p.wait_prof + (size_t)blockIdx.x * 16;
     for (int i = 0; i < 15; ++i)
       if (gbw[i] != 0) o[i] = gbw[i];
