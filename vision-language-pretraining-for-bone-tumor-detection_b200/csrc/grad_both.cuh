@@ -13,6 +13,11 @@
 //       acc[128 x d] += G (A, K-major) * T_j (B, MN-major), accumulator resident over the row sweep;
 //   * the dT consumer that currently owns column j reads the SAME bytes as the MN-major operand G^T:
 //       acc[128 x d] += G^T (A, MN-major) * I_i (B, MN-major).
+// Every role issues its MMAs from ONE elected thread that runs the whole loop (umma_*_stage_peek: the
+// next stage's barrier test, the stage's MMAs and their commit in one asm block, descriptors advanced
+// by 32-bit adds): with a per-stage elect.sync region and rebuilt descriptors the issue path, not the
+// tensor pipe, bounded the tile (profiles/r02_issue_path.txt).  The staged tile's generic -> async
+// proxy fence is executed once, by the store warp, not by the 16 softmax warps.
 // Flags in global memory carry the hand-off: `ready` (tile stored) is a RELEASE store behind a proxy
 // fence -- a relaxed flag was measured to overtake the bulk store's bytes now and then (a few stale
 // rows per ~10 launches); two store warps alternate so that the ~2500-cycle fence never sits between
