@@ -171,3 +171,22 @@ def test_rank_and_stable_topk_formulation_equals_the_reference_topk_metrics():
     q = torch.tensor([[1.0, 0.0]]); kk = torch.tensor([[1.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
     assert O.retrieval_topk(q, kk, 3)[0].tolist() == [0, 1, 2]
     assert O.retrieval_ranks(torch.cat([q, q]), kk).tolist() == [0, 1]
+
+
+def test_duplicate_caption_mask_matches_the_reference_get_mask(golden_dir):
+    """`oracle.reference_get_mask` (and the id mapping of the drop-in module) against the mask that the
+    REFERENCE'S OWN `_get_mask` source (lines 506-530, executed by tests/golden/make_golden_mask.py)
+    returns for a list of caption strings with duplicates."""
+    g = np.load(os.path.join(golden_dir, "mask_captions.npz"))
+    captions = [str(c) for c in g["captions"]]
+    ref_mask = torch.from_numpy(g["mask"])
+    assert tuple(int(v) for v in g["lines"]) == (506, 530)
+    # ids the way the reference builds them (:520-521) ...
+    uniq = {c: i for i, c in enumerate(sorted(set(captions)))}
+    ids = torch.tensor([uniq[c] for c in captions])
+    assert torch.equal(O.reference_get_mask(ids), ref_mask)
+    # ... and the way the drop-in module builds them (crc32: consistent across ranks without communication)
+    import zlib
+    ids2 = torch.tensor([zlib.crc32(c.encode("utf-8")) & 0x7FFFFFFF for c in captions], dtype=torch.int32)
+    assert torch.equal(O.reference_get_mask(ids2), ref_mask)
+    assert int((ref_mask == 0).sum()) > 0 and bool((ref_mask.diagonal() == 1).all())
