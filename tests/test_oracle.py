@@ -190,3 +190,19 @@ def test_duplicate_caption_mask_matches_the_reference_get_mask(golden_dir):
     ids2 = torch.tensor([zlib.crc32(c.encode("utf-8")) & 0x7FFFFFFF for c in captions], dtype=torch.int32)
     assert torch.equal(O.reference_get_mask(ids2), ref_mask)
     assert int((ref_mask == 0).sum()) > 0 and bool((ref_mask.diagonal() == 1).all())
+
+
+def test_retrieval_metric_oracle_matches_the_reference_source(golden_dir):
+    """`oracle.recall_at_k_on_image_text_retrieval` / `precision_at_k_on_image_embeddings` against the values
+    the REFERENCE'S OWN methods (lines 364-439, executed by tests/golden/make_golden_retrieval.py) return
+    on seeded embeddings."""
+    g = np.load(os.path.join(golden_dir, "retrieval_metrics.npz"))
+    assert [int(v) for v in g["lines"]] == [364, 400, 402, 439]
+    for tag in ("a", "b"):
+        n, d, rho, seed = g[f"{tag}_params"]
+        img, txt = O.make_embeddings(int(n), int(d), rho=float(rho), seed=int(seed))
+        labels = torch.from_numpy(np.random.default_rng(int(seed)).integers(0, 7, size=int(n)))
+        r = O.recall_at_k_on_image_text_retrieval(img, txt, [1, 3, 5, 10])
+        p = O.precision_at_k_on_image_embeddings(img, labels, [3, 5, 10, 15])
+        assert [r[k] for k in (1, 3, 5, 10)] == list(g[f"{tag}_recall"])
+        assert [p[k] for k in (3, 5, 10, 15)] == list(g[f"{tag}_precision"])
