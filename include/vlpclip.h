@@ -149,10 +149,9 @@ int vlpclip_loss_finish(const float* sums2, int n_global, float* out3, void* str
  * CUDA events on their stream (enable = 1) and read the duration of the latest call in ms */
 int vlpclip_time_grad_kernel(int enable);
 float vlpclip_last_grad_kernel_ms(void);
-/* development builds only (-DVLP_PROFILE_WAITS; tools/wait_profile.py, tools/pipeline_experiments.py):
- * device buffer of [74 SM pairs][16] int64 in which the next backward kernels record, per role, the
- * cycles spent blocked on each pipeline barrier (the staged kernels of csrc/next/ append
- * [148 SMs][8] int64 for the forward kernel); a no-op in the shipped library */
+/* development builds only (-DVLP_PROFILE_WAITS; tools/check_grad_both.py --prof, tools/wait_profile.py):
+ * device buffer of [SMs][16] int64 in which the next backward kernels record, per role, the cycles
+ * spent blocked on each pipeline barrier; a no-op in the shipped library */
 int vlpclip_dev_set_wait_profile(void* buf);
 
 /* host-only: the backward's work partition for n_clusters SM pairs (see grad_bwd.cu, "stream-K").

@@ -52,7 +52,7 @@ def main():
     i16, t16 = VF.cast_bf16_to_f16(I), VF.cast_bf16_to_f16(T)
     for _ in range(2):
         VF._grad(i16, t16, r_stats, c_stats, s, 0, n, 1.0, 1.0, True)
-    # [74][16] backward counters, then [148][8] forward counters (tools/pipeline_experiments.py prints both)
+    # [74][16] counters of the two-pass backward (grad_pair_kernel); the rest of the buffer is unused
     prof_all = torch.zeros(74 * 16 + 148 * 8, dtype=torch.int64, device=dev)
     prof = prof_all[:74 * 16].view(74, 16)
     lib.vlpclip_dev_set_wait_profile(prof_all.data_ptr())

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libvlpclip.so")
 # VLP_B200_LIB=/path/to/other.so loads that library instead (same C ABI) and never rebuilds it: lets the
-# whole GPU test-suite and bench.py run against a staged variant of tools/pipeline_experiments.py
+# whole GPU test-suite and bench.py run against an experimental build (e.g. one of tools/diag_build.sh)
 # before it is promoted.  Unset (the default) = the shipped library built from csrc/*.cu.
 _LIB_OVERRIDE = os.environ.get("VLP_B200_LIB") or None
 if _LIB_OVERRIDE:
